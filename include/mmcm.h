@@ -1,0 +1,146 @@
+/*
+ * mmcm.h -- C ABI of the B200-native scoring path (libmmcm.so).
+ *
+ * Drop-in boundary: the reference's scoring hot path is
+ *     outputs = model(**batch); logits = outputs["logits"]
+ * (R/scripts/evaluate.py:168-178, R/scripts/inference.py:214-216, R/sagemaker/inference.py:277-279),
+ * i.e. `MultiModalFusionClassifier.forward` (R/src/models/fusion.py:157-229) and
+ * `MultiTaskClassifier.forward` (R/src/models/multitask.py:156-227), whose encoder arithmetic is
+ * Hugging Face `transformers` CLIP / SigLIP (HF/models/clip/modeling_clip.py,
+ * HF/models/siglip/modeling_siglip.py).  The reference has no FFI of its own (pure Python); these
+ * entry points are what a ctypes binding on the reference side calls -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, non-zero on failure; mmcm_last_error() gives the message
+ *     (thread-local).  Codes: 1 = invalid argument (Python side raises ValueError, mirroring
+ *     HF/models/clip/modeling_clip.py:204-207,243-247), 2 = CUDA error / no device (RuntimeError),
+ *     3 = state error (weights missing, handle not finalized).
+ *   - device pointers are BORROWED: the caller keeps them alive until the work enqueued on `stream`
+ *     has completed.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - a handle is bound to one device and is not thread-safe; use one handle per process/GPU.
+ *   - there is no CPU fallback: without a CUDA device mmcm_create fails with code 2.
+ */
+#ifndef MMCM_H_
+#define MMCM_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MMCM_API __attribute__((visibility("default")))
+#else
+#define MMCM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMCM_OK 0
+#define MMCM_EINVAL 1
+#define MMCM_ECUDA 2
+#define MMCM_ESTATE 3
+
+#define MMCM_BACKEND_CLIP 0   /* fusion.py:100-108  CLIPModel                    */
+#define MMCM_BACKEND_SIGLIP 1 /* fusion.py:109-127  AutoModel (SigLIP / SigLIP2)   */
+#define MMCM_HEAD_FUSION 0    /* R/src/models/fusion.py  MultiModalFusionClassifier */
+#define MMCM_HEAD_MTL 1       /* R/src/models/multitask.py MultiTaskClassifier      */
+#define MMCM_ACT_QUICK_GELU 1 /* HF/activations.py:122-123 */
+#define MMCM_ACT_GELU_TANH 2  /* HF/activations.py:45      */
+
+typedef struct mmcm_handle_s* mmcm_handle;
+
+/* Shapes of one model instance.  Mirrors CLIPConfig / SiglipConfig plus the head ctor kwargs
+ * (fusion.py:83-95, multitask.py:40-52). */
+typedef struct mmcm_config {
+  int32_t backend;          /* MMCM_BACKEND_*                               */
+  int32_t head;             /* MMCM_HEAD_*                                  */
+  int32_t text_hidden, text_heads, text_layers, text_ffn, text_act;
+  int32_t vis_hidden, vis_heads, vis_layers, vis_ffn, vis_act;
+  float text_eps, vis_eps;
+  int32_t vocab, max_pos;   /* text vocabulary and positions (77 / 64)      */
+  int32_t eos_id;           /* CLIP pooling id; 2 = legacy argmax branch    */
+  int32_t image, patch;     /* 224, 32 | 16                                 */
+  int32_t proj_dim;         /* CLIP projection_dim / SigLIP projection_size */
+  int32_t fusion_dim;       /* 512                                          */
+  int32_t num_outputs;      /* num_labels (fusion) or number of tasks (mtl) */
+  int32_t head_hidden_dim;  /* mtl: 0 => Linear(fusion_dim,1) heads         */
+} mmcm_config;
+
+/* Lifetime ------------------------------------------------------------------------------------ */
+MMCM_API int mmcm_create(const mmcm_config* cfg, int device, mmcm_handle* out);
+MMCM_API int mmcm_destroy(mmcm_handle h);
+
+/* Weights: one call per state-dict entry, `key` is the reference's own key
+ * ("backbone.text_model.encoder.layers.3.self_attn.q_proj.weight", "cls.1.bias", ... -- the names
+ * `model.load_state_dict` consumes at R/scripts/evaluate.py:139-151).  `src` is fp32, host or device
+ * memory, `numel` elements; the library keeps its own repacked copy (bf16 GEMM operands with Q/K/V
+ * concatenated and 1/sqrt(dh) folded into Q; fp32 for norms, biases, embeddings' positions and heads).
+ * Unknown keys that the path does not consume (logit_scale, logit_bias, pos_weight, log_vars) are
+ * accepted and ignored; anything else returns MMCM_EINVAL. */
+MMCM_API int mmcm_load_weight(mmcm_handle h, const char* key, const float* src, int64_t numel);
+/* Verifies that every tensor of the configured model was loaded and builds the TMA descriptors. */
+MMCM_API int mmcm_finalize_weights(mmcm_handle h);
+
+/* The hot path.  Replaces MultiModalFusionClassifier.forward / MultiTaskClassifier.forward
+ * (fusion.py:157-216, multitask.py:156-207): all pointers are DEVICE pointers.
+ *   input_ids      int64 [B,S]            attention_mask int64 [B,S] or NULL (== all ones)
+ *   pixel_values   fp32  [B,3,image,image]
+ *   text_present   fp32  [B]              image_present  fp32 [B]
+ *   logits_out     fp32  [B,num_outputs]  probs_out      fp32 [B,num_outputs] or NULL (sigmoid(logits),
+ *                                          the callers' post-processing, inference.py:218)
+ * S must be <= max_pos (else MMCM_EINVAL, like HF's ValueError). Work is enqueued on `stream`. */
+MMCM_API int mmcm_forward(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                 const float* pixel_values, const float* text_present, const float* image_present,
+                 int32_t B, int32_t S, float* logits_out, float* probs_out, void* stream);
+
+/* Same call with HOST buffers (pinned memory recommended): copies inputs H2D, runs the path, copies
+ * logits (and probs) back and synchronises `stream` before returning.  This is the end-to-end call a
+ * CPU-side caller such as sagemaker/inference.py:predict_fn would bind. */
+MMCM_API int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                      const float* pixel_values, const float* text_present, const float* image_present,
+                      int32_t B, int32_t S, float* logits_out, float* probs_out, void* stream);
+
+/* Introspection ------------------------------------------------------------------------------ */
+/* Copies an intermediate of the LAST forward into dst (device fp32).  Names: "text_pooled",
+ * "vision_pooled" (tower pooler_output, fp32 [B,D]), "text_hidden", "vision_hidden" (residual stream
+ * after the last layer, fp32 [B*T,D]).  *numel_out receives the element count. */
+MMCM_API int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity, int64_t* numel_out,
+                   void* stream);
+/* Number of kernels this library launched during the last mmcm_forward on this handle. */
+MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
+/* CUDA-event time (ms) of the GEMM launches of the last forward when profiling was enabled with
+ * mmcm_set_option(h, "time_gemms", 1); also returns their FLOPs. Synchronises the device. */
+MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
+/* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05, 1 = SIMT validation kernel),
+ * "micro_batch" (samples per internal pass), "streams" (1 or 2: text/vision towers on separate streams). */
+MMCM_API int mmcm_set_option(mmcm_handle h, const char* name, int64_t value);
+MMCM_API const char* mmcm_last_error(void);
+MMCM_API const char* mmcm_version(void);
+
+/* Stand-alone kernels (unit parity tests call these through the same ABI) ----------------------- */
+#define MMCM_EPI_BIAS_BF16 0       /* out bf16 = acc + bias                                  */
+#define MMCM_EPI_BIAS_ACT_BF16 1   /* out bf16 = act(acc + bias)                             */
+#define MMCM_EPI_BIAS_RESID_F32 2  /* out fp32 = acc + bias + resid (resid may alias out)    */
+#define MMCM_EPI_PATCH_F32 3       /* out fp32[(r/P)*T+off+r%P] = acc + bias? + pos[off+r%P] */
+
+/* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): A, W bf16 row-major device pointers (K % 64 == 0, N % 128 == 0).
+ * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT validation kernel. act = MMCM_ACT_* for EPI_BIAS_ACT.
+ * For EPI_PATCH: pos fp32 [T,N], P = patches per sample, T = tokens per sample, off = T - P. */
+MMCM_API int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K,
+                   int32_t epilogue, int32_t act, void* out, const float* resid, const float* pos,
+                   int32_t P, int32_t T, int32_t impl, void* stream);
+/* y = LayerNorm(x) over the last dim D (512 or 768); x fp32 [rows,D]; out_bf16 and/or out_f32 may be NULL. */
+MMCM_API int mmcm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
+                   void* out_bf16, float* out_f32, void* stream);
+/* Multi-head attention over a packed QKV buffer bf16 [B*T, 3*D] (Q pre-scaled by 1/sqrt(64)); head dim 64.
+ * key_valid uint8 [B,T] or NULL; causal 0/1; out bf16 [B*T, D]. A query with no admissible key yields 0. */
+MMCM_API int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B, int32_t T, int32_t heads,
+                   int32_t causal, void* out, void* stream);
+/* fp32 -> bf16 with scale (device pointers), used by tests to prepare operands. */
+MMCM_API int mmcm_cast_bf16(const float* src, void* dst, int64_t n, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMCM_H_ */

@@ -1,0 +1,243 @@
+"""Architecture tables and parameter specs for the scoring hot path.
+
+The reference builds its towers with ``CLIPModel.from_pretrained(encoder_name)`` /
+``AutoModel.from_pretrained(encoder_name)`` (R/src/models/fusion.py:100-127,
+R/src/models/multitask.py:60-89).  The arithmetic of those towers lives in the third-party
+``transformers`` package (HF/models/clip/modeling_clip.py, HF/models/siglip/modeling_siglip.py);
+here we only need their *shapes* and *state-dict key names* so that checkpoints written by the
+reference (`model.safetensors`, R/scripts/evaluate.py:139-151) load unchanged.
+
+Nothing in this file touches CUDA.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, asdict
+from typing import Dict, List, Tuple
+
+# activation ids shared with csrc/common.cuh (enum Act)
+ACT_QUICK_GELU = 1   # HF/activations.py:122-123   x * sigmoid(1.702 x)
+ACT_GELU_TANH = 2    # HF/activations.py:45        gelu(approximate="tanh")
+
+BACKEND_CLIP = 0
+BACKEND_SIGLIP = 1
+
+HEAD_FUSION = 0
+HEAD_MTL = 1
+
+
+@dataclass(frozen=True)
+class TowerCfg:
+    hidden: int
+    heads: int
+    layers: int
+    ffn: int
+    eps: float
+    act: int
+
+
+@dataclass(frozen=True)
+class ArchCfg:
+    """Everything the C side needs to size its arenas (mirrors `mmcm_config` in include/mmcm.h)."""
+    backend: int
+    text: TowerCfg
+    vision: TowerCfg
+    vocab: int
+    max_pos: int          # text positions (77 CLIP, 64 SigLIP)
+    eos_id: int           # CLIP EOS pooling id; -1 => SigLIP last-token pooling
+    image: int
+    patch: int
+    proj_dim: int         # CLIP projection_dim (512); SigLIP text projection_size (768)
+
+    @property
+    def n_patches(self) -> int:
+        return (self.image // self.patch) ** 2
+
+    @property
+    def vis_tokens(self) -> int:  # CLIP prepends a class token, SigLIP does not
+        return self.n_patches + (1 if self.backend == BACKEND_CLIP else 0)
+
+
+# HF/models/clip/configuration_clip.py:47-64,97-109 (defaults == openai/clip-vit-base-patch32)
+CLIP_B32 = ArchCfg(
+    backend=BACKEND_CLIP,
+    text=TowerCfg(512, 8, 12, 2048, 1e-5, ACT_QUICK_GELU),
+    vision=TowerCfg(768, 12, 12, 3072, 1e-5, ACT_QUICK_GELU),
+    vocab=49408, max_pos=77, eos_id=49407, image=224, patch=32, proj_dim=512,
+)
+CLIP_B16 = ArchCfg(
+    backend=BACKEND_CLIP,
+    text=TowerCfg(512, 8, 12, 2048, 1e-5, ACT_QUICK_GELU),
+    vision=TowerCfg(768, 12, 12, 3072, 1e-5, ACT_QUICK_GELU),
+    vocab=49408, max_pos=77, eos_id=49407, image=224, patch=16, proj_dim=512,
+)
+# HF/models/siglip/configuration_siglip.py:34-48,77-86; vocab 256000 = siglip2 Gemma tokenizer
+SIGLIP2_B16 = ArchCfg(
+    backend=BACKEND_SIGLIP,
+    text=TowerCfg(768, 12, 12, 3072, 1e-6, ACT_GELU_TANH),
+    vision=TowerCfg(768, 12, 12, 3072, 1e-6, ACT_GELU_TANH),
+    vocab=256000, max_pos=64, eos_id=-1, image=224, patch=16, proj_dim=768,
+)
+
+_BY_NAME = {
+    "openai/clip-vit-base-patch32": CLIP_B32,
+    "openai/clip-vit-base-patch16": CLIP_B16,
+    "google/siglip2-base-patch16-224": SIGLIP2_B16,
+    "google/siglip-base-patch16-224": SIGLIP2_B16,
+}
+
+
+def resolve_arch(encoder_name: str, backend: str) -> ArchCfg:
+    """Map the reference's `encoder_name` (R/config/*.yaml `model.encoder_name`) to shapes."""
+    if encoder_name in _BY_NAME:
+        cfg = _BY_NAME[encoder_name]
+    else:
+        low = encoder_name.lower()
+        if "siglip" in low:
+            cfg = SIGLIP2_B16
+        elif "patch16" in low:
+            cfg = CLIP_B16
+        else:
+            cfg = CLIP_B32
+    want = BACKEND_CLIP if backend.lower() == "clip" else BACKEND_SIGLIP
+    if cfg.backend != want:
+        raise ValueError(
+            f"encoder_name={encoder_name!r} is a {'clip' if cfg.backend == BACKEND_CLIP else 'siglip'} "
+            f"architecture but backend={backend!r} was requested")
+    return cfg
+
+
+Spec = List[Tuple[str, Tuple[int, ...]]]
+
+
+def _tower_layer_spec(prefix: str, t: TowerCfg) -> Spec:
+    d, f = t.hidden, t.ffn
+    out: Spec = []
+    for i in range(t.layers):
+        p = f"{prefix}encoder.layers.{i}."
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            out += [(p + f"self_attn.{nm}.weight", (d, d)), (p + f"self_attn.{nm}.bias", (d,))]
+        out += [(p + "layer_norm1.weight", (d,)), (p + "layer_norm1.bias", (d,)),
+                (p + "mlp.fc1.weight", (f, d)), (p + "mlp.fc1.bias", (f,)),
+                (p + "mlp.fc2.weight", (d, f)), (p + "mlp.fc2.bias", (d,)),
+                (p + "layer_norm2.weight", (d,)), (p + "layer_norm2.bias", (d,))]
+    return out
+
+
+def text_tower_spec(prefix: str, a: ArchCfg) -> Spec:
+    """Keys of `CLIPTextTransformer` / `SiglipTextTransformer` under `prefix` (ends with 'text_model.')."""
+    d = a.text.hidden
+    s: Spec = [(prefix + "embeddings.token_embedding.weight", (a.vocab, d)),
+               (prefix + "embeddings.position_embedding.weight", (a.max_pos, d))]
+    s += _tower_layer_spec(prefix, a.text)
+    s += [(prefix + "final_layer_norm.weight", (d,)), (prefix + "final_layer_norm.bias", (d,))]
+    if a.backend == BACKEND_SIGLIP:
+        s += [(prefix + "head.weight", (a.proj_dim, d)), (prefix + "head.bias", (a.proj_dim,))]
+    return s
+
+
+def vision_tower_spec(prefix: str, a: ArchCfg) -> Spec:
+    """Keys of `CLIPVisionTransformer` / `SiglipVisionTransformer` under `prefix` (ends with 'vision_model.')."""
+    d, f = a.vision.hidden, a.vision.ffn
+    s: Spec = []
+    if a.backend == BACKEND_CLIP:
+        s += [(prefix + "embeddings.class_embedding", (d,)),
+              (prefix + "embeddings.patch_embedding.weight", (d, 3, a.patch, a.patch)),
+              (prefix + "embeddings.position_embedding.weight", (a.vis_tokens, d)),
+              (prefix + "pre_layrnorm.weight", (d,)), (prefix + "pre_layrnorm.bias", (d,))]
+    else:
+        s += [(prefix + "embeddings.patch_embedding.weight", (d, 3, a.patch, a.patch)),
+              (prefix + "embeddings.patch_embedding.bias", (d,)),
+              (prefix + "embeddings.position_embedding.weight", (a.vis_tokens, d))]
+    s += _tower_layer_spec(prefix, a.vision)
+    s += [(prefix + "post_layernorm.weight", (d,)), (prefix + "post_layernorm.bias", (d,))]
+    if a.backend == BACKEND_SIGLIP:
+        h = prefix + "head."
+        s += [(h + "probe", (1, 1, d)),
+              (h + "attention.in_proj_weight", (3 * d, d)), (h + "attention.in_proj_bias", (3 * d,)),
+              (h + "attention.out_proj.weight", (d, d)), (h + "attention.out_proj.bias", (d,)),
+              (h + "layernorm.weight", (d,)), (h + "layernorm.bias", (d,)),
+              (h + "mlp.fc1.weight", (f, d)), (h + "mlp.fc1.bias", (f,)),
+              (h + "mlp.fc2.weight", (d, f)), (h + "mlp.fc2.bias", (d,))]
+    return s
+
+
+def fusion_spec(a: ArchCfg, num_labels: int, fusion_dim: int) -> Spec:
+    """State-dict layout of the reference's MultiModalFusionClassifier (R/src/models/fusion.py:129-147)."""
+    s: Spec = []
+    if a.backend == BACKEND_CLIP:
+        s.append(("backbone.logit_scale", ()))
+    else:
+        s += [("backbone.logit_scale", (1,)), ("backbone.logit_bias", (1,))]
+    s += text_tower_spec("backbone.text_model.", a)
+    s += vision_tower_spec("backbone.vision_model.", a)
+    if a.backend == BACKEND_CLIP:
+        s += [("backbone.visual_projection.weight", (a.proj_dim, a.vision.hidden)),
+              ("backbone.text_projection.weight", (a.proj_dim, a.text.hidden))]
+    d, fd = a.proj_dim, fusion_dim
+    s += [("proj_t.weight", (fd, d)), ("proj_t.bias", (fd,)),
+          ("proj_i.weight", (fd, d)), ("proj_i.bias", (fd,)),
+          ("g_t.weight", (fd, fd)), ("g_t.bias", (fd,)),
+          ("g_i.weight", (fd, fd)), ("g_i.bias", (fd,)),
+          ("gate.weight", (fd, 2 * fd + 2)), ("gate.bias", (fd,)),
+          ("cls.0.weight", (5 * fd,)), ("cls.0.bias", (5 * fd,)),
+          ("cls.1.weight", (fd, 5 * fd)), ("cls.1.bias", (fd,)),
+          ("cls.4.weight", (num_labels, fd)), ("cls.4.bias", (num_labels,)),
+          ("ln_fused.weight", (fd,)), ("ln_fused.bias", (fd,))]
+    return s
+
+
+def mtl_spec(a: ArchCfg, num_tasks: int, fusion_dim: int, head_hidden_dim: int) -> Spec:
+    """State-dict layout of the reference's MultiTaskClassifier, clip backend (R/src/models/multitask.py:59-117)."""
+    if a.backend != BACKEND_CLIP:
+        # R/src/models/multitask.py:81-88 asserts for AutoModel backends (SURVEY §8b defect iii)
+        raise AssertionError("Could not infer hidden sizes for AutoModel backend.")
+    s: Spec = []
+    s += text_tower_spec("tower_txt.text_model.", a)
+    s += vision_tower_spec("tower_img.vision_model.", a)
+    fd = fusion_dim
+    s += [("proj_t.weight", (fd, a.text.hidden)), ("proj_t.bias", (fd,)),
+          ("proj_i.weight", (fd, a.vision.hidden)), ("proj_i.bias", (fd,)),
+          ("g_t.weight", (fd, fd)), ("g_t.bias", (fd,)),
+          ("g_i.weight", (fd, fd)), ("g_i.bias", (fd,)),
+          ("gate.weight", (fd, 2 * fd + 2)), ("gate.bias", (fd,)),
+          ("shared_head.1.weight", (fd, fd)), ("shared_head.1.bias", (fd,))]
+    for j in range(num_tasks):
+        if head_hidden_dim and head_hidden_dim > 0:
+            s += [(f"heads.{j}.0.weight", (head_hidden_dim, fd)), (f"heads.{j}.0.bias", (head_hidden_dim,)),
+                  (f"heads.{j}.3.weight", (1, head_hidden_dim)), (f"heads.{j}.3.bias", (1,))]
+        else:
+            s += [(f"heads.{j}.weight", (1, fd)), (f"heads.{j}.bias", (1,))]
+    return s
+
+
+# ---- algorithmic work: 2*M*N*K per Linear/conv on all tokens + 4*T^2*dh*H per attention layer
+def _tower_flops(t: TowerCfg, tokens: int) -> float:
+    d, f = t.hidden, t.ffn
+    per_tok = 2.0 * (4 * d * d + 2 * d * f)
+    attn = 4.0 * tokens * tokens * d
+    return t.layers * (tokens * per_tok + attn)
+
+
+def algorithmic_flops_per_sample(a: ArchCfg, head: int, num_labels: int = 5, fusion_dim: int = 512,
+                                 head_hidden_dim: int = 0) -> Dict[str, float]:
+    pt = a.n_patches
+    vis = 2.0 * pt * (3 * a.patch * a.patch) * a.vision.hidden + _tower_flops(a.vision, a.vis_tokens)
+    txt = _tower_flops(a.text, a.max_pos)
+    fd = fusion_dim
+    if a.backend == BACKEND_SIGLIP:
+        d, f = a.vision.hidden, a.vision.ffn
+        # MAP head: K/V projections over all tokens + 1-query attention + out_proj + MLP
+        vis += 2.0 * pt * d * 2 * d + 2.0 * d * d * 2 + 4.0 * pt * d + 2.0 * 2 * d * f
+        txt += 2.0 * a.text.hidden * a.proj_dim
+    if head == HEAD_FUSION:
+        if a.backend == BACKEND_CLIP:
+            vis += 2.0 * a.vision.hidden * a.proj_dim
+            txt += 2.0 * a.text.hidden * a.proj_dim
+        hd = 2.0 * (2 * a.proj_dim * fd + 2 * fd * fd + (2 * fd + 2) * fd + 5 * fd * fd + fd * num_labels)
+    else:
+        hd = 2.0 * (a.text.hidden * fd + a.vision.hidden * fd + 2 * fd * fd + (2 * fd + 2) * fd + fd * fd)
+        if head_hidden_dim:
+            hd += 2.0 * num_labels * (fd * head_hidden_dim + head_hidden_dim)
+        else:
+            hd += 2.0 * num_labels * fd
+    return {"vision": vis, "text": txt, "head": hd, "total": vis + txt + hd}

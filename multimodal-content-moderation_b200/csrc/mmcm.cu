@@ -1,0 +1,1144 @@
+// libmmcm.so -- the C ABI declared in include/mmcm.h and the host-side engine behind it.
+//
+// The engine owns (a) a repacked copy of the reference's state dict (bf16 GEMM operands with Q|K|V concatenated
+// and dh^-1/2 folded into Q; fp32 norms, biases, embeddings and heads) and (b) a per-tower activation arena sized for
+// one micro-batch.  mmcm_forward enqueues, per micro-batch, the text tower on one stream and the vision tower on a
+// second one, joins them on the caller's stream and runs the fused head kernel over the whole batch.
+//
+// Reference call stack this replaces: R/src/models/fusion.py:157-216 / R/src/models/multitask.py:156-207 and, below
+// them, HF/models/clip/modeling_clip.py (CLIPTextTransformer :531-589, CLIPVisionTransformer :667-691, encoder layer
+// :363-384) and HF/models/siglip/modeling_siglip.py (:489-527, :604-649).
+//
+// There is NO CPU path in this file: without a CUDA device every entry point fails with MMCM_ECUDA.
+#include "../../include/mmcm.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "heads.cuh"
+#include "rowwise.cuh"
+
+using namespace mmcm;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(expr)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return fail(MMCM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(expr)                 \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != MMCM_OK) return _r; \
+  } while (0)
+
+static int g_num_sms = kNumSMs;
+
+// cudaFuncSetAttribute is per device: remember which devices a given kernel instantiation was configured on
+struct AttrOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::mutex g_mu;
+
+static int ensure_driver() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encode) return MMCM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+    return fail(MMCM_ECUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
+  }
+  return MMCM_OK;
+}
+
+// K-major bf16 matrix [rows, K] -> 2D map with a (64 x box_rows) box, 128-byte swizzle; out-of-range rows read as 0.
+static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows, bool weight) {
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        weight ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMCM_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld", (int)r,
+                                     (long long)rows, (long long)K);
+  return MMCM_OK;
+}
+
+struct TmapKey {
+  const void* p;
+  int64_t rows, K;
+  int box;
+  bool operator<(const TmapKey& o) const { return std::tie(p, rows, K, box) < std::tie(o.p, o.rows, o.K, o.box); }
+};
+static std::map<TmapKey, CUtensorMap> g_tmaps;
+
+static int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box, bool weight) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  TmapKey k{ptr, rows, K, box};
+  auto it = g_tmaps.find(k);
+  if (it == g_tmaps.end()) {
+    CUtensorMap m;
+    CKR(make_tmap(&m, ptr, rows, K, box, weight));
+    if (g_tmaps.size() > 8192) g_tmaps.clear();
+    it = g_tmaps.emplace(k, m).first;
+  }
+  *out = it->second;
+  return MMCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launch counting
+struct LaunchStats {
+  int64_t launches = 0;
+  bool time_gemms = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  double gemm_flops = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ GEMM launcher
+template <int BN, int EPI>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, int M, int N, int K,
+                     cudaStream_t st) {
+  using C = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  static AttrOnce once;
+  if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+  CK(cudaGetLastError());
+  return MMCM_OK;
+}
+
+template <int EPI>
+static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, const EpiParams& ep, int impl,
+                           cudaStream_t st) {
+  if (impl == 1) {
+    dim3 grid(N / 32, (M + 31) / 32);
+    gemm_simt_kernel<EPI><<<grid, 256, 0, st>>>(A, W, ep, M, N, K);
+    CK(cudaGetLastError());
+    return MMCM_OK;
+  }
+  CKR(ensure_driver());
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  CKR(get_tmap(&ta, A, M, K, 128, false));
+  CKR(get_tmap(&tb, W, N, K, BN, true));
+  if (BN == 256) return launch_tc<256, EPI>(ta, tb, ep, M, N, K, st);
+  return launch_tc<128, EPI>(ta, tb, ep, M, N, K, st);
+}
+
+static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int epi, const EpiParams& ep, int impl,
+                       cudaStream_t st, LaunchStats* stats) {
+  if (M <= 0) return MMCM_OK;
+  if (N % 128 != 0 || K % 64 != 0 || N <= 0 || K <= 0)
+    return fail(MMCM_EINVAL, "gemm: need N %% 128 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (stats && stats->time_gemms) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+  }
+  int r;
+  switch (epi) {
+    case EPI_BIAS_BF16: r = launch_gemm_epi<EPI_BIAS_BF16>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_BIAS_ACT_BF16: r = launch_gemm_epi<EPI_BIAS_ACT_BF16>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_BIAS_RESID_F32: r = launch_gemm_epi<EPI_BIAS_RESID_F32>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_PATCH_F32: r = launch_gemm_epi<EPI_PATCH_F32>(A, W, M, N, K, ep, impl, st); break;
+    default: return fail(MMCM_EINVAL, "gemm: unknown epilogue %d", epi);
+  }
+  CKR(r);
+  if (stats) {
+    stats->launches++;
+    if (stats->time_gemms) {
+      CK(cudaEventRecord(e1, st));
+      stats->gemm_events.emplace_back(e0, e1);
+      stats->gemm_flops += 2.0 * M * (double)N * K;
+    }
+  }
+  return MMCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ other launchers
+static int launch_layernorm(const float* x, const float* g, const float* b, float eps, int rows, int D,
+                            const int* gather, bf16* out_bf16, float* out_f32, cudaStream_t st, LaunchStats* stats) {
+  if (rows <= 0) return MMCM_OK;
+  const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+  if (D == 512) layernorm_kernel<512><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
+  else if (D == 768) layernorm_kernel<768><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
+  else if (D == 1024) layernorm_kernel<1024><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
+  else return fail(MMCM_EINVAL, "layernorm: unsupported width %d (512, 768, 1024)", D);
+  CK(cudaGetLastError());
+  if (stats) stats->launches++;
+  return MMCM_OK;
+}
+
+template <int TPAD, int QW>
+static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, int T, int heads, int causal,
+                      cudaStream_t st) {
+  auto kern = attention_kernel<TPAD, QW>;
+  constexpr int smem = attention_smem_bytes<TPAD, QW>();
+  static AttrOnce once;
+  if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int qblocks = (TPAD / 16 + QW - 1) / QW;
+  dim3 grid(heads, B, qblocks);
+  kern<<<grid, QW * 32, smem, st>>>(qkv, out, kvalid, nullptr, nullptr, T, heads * ATT_DH, causal, T);
+  CK(cudaGetLastError());
+  return MMCM_OK;
+}
+
+static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
+                            cudaStream_t st, LaunchStats* stats) {
+  if (B <= 0) return MMCM_OK;
+  int r;
+  if (T <= 16) r = launch_att<16, 1>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 32) r = launch_att<32, 2>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 64) r = launch_att<64, 4>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 80) r = launch_att<80, 5>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 128) r = launch_att<128, 8>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 208) r = launch_att<208, 7>(qkv, out, kvalid, B, T, heads, causal, st);
+  else if (T <= 256) r = launch_att<256, 8>(qkv, out, kvalid, B, T, heads, causal, st);
+  else return fail(MMCM_EINVAL, "attention: sequence length %d > 256 is not supported", T);
+  CKR(r);
+  if (stats) stats->launches++;
+  return MMCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+struct Part {          // one rectangular piece of a state-dict tensor and where it goes
+  int64_t src_off;     // element offset into the source tensor
+  int64_t rows, cols;  // piece shape
+  int64_t src_pitch;   // elements between consecutive source rows
+  void* dst;
+  int64_t dst_pitch;
+  int kind;            // 0 = fp32, 1 = bf16
+  float scale;
+};
+struct Slot {
+  int64_t numel = 0;
+  std::vector<Part> parts;
+  bool loaded = false;
+};
+
+__global__ void copy2d_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t rows, int64_t cols,
+                              int64_t src_pitch, int64_t dst_pitch, int kind, float scale) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float v = src[r * src_pitch + c] * scale;
+    if (kind == 1) reinterpret_cast<bf16*>(dst)[r * dst_pitch + c] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[r * dst_pitch + c] = v;
+  }
+}
+
+struct LayerW {
+  bf16 *wqkv, *wo, *w1, *w2;
+  float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+struct TowerW {
+  int D, H, L, F, act;
+  float eps;
+  std::vector<LayerW> layers;
+};
+
+struct Arena {  // activations of one tower for one micro-batch
+  float* x = nullptr;    // fp32 residual stream [rows, D]
+  bf16* h = nullptr;     // LayerNorm output     [rows, D]
+  bf16* qkv = nullptr;   // [rows, 3D]
+  bf16* att = nullptr;   // [rows, D]
+  bf16* ff = nullptr;    // [rows, F]
+  int* pool_row = nullptr;
+  int64_t rows = 0;
+};
+
+struct mmcm_handle_s {
+  mmcm_config cfg;
+  int device = 0;
+  std::vector<void*> allocs;
+  std::unordered_map<std::string, Slot> slots;
+  bool finalized = false;
+
+  TowerW text, vis;
+  // text extras
+  float *tok_emb = nullptr, *tpos_emb = nullptr, *tfin_g = nullptr, *tfin_b = nullptr;
+  float *thead_w = nullptr, *thead_b = nullptr;  // siglip text head
+  // vision extras
+  bf16* wpatch = nullptr;
+  float *bpatch = nullptr, *cls_emb = nullptr, *vpos_emb = nullptr, *pre_g = nullptr, *pre_b = nullptr,
+        *post_g = nullptr, *post_b = nullptr;
+  // siglip MAP head
+  float *map_probe = nullptr, *map_inw = nullptr, *map_inb = nullptr, *map_q = nullptr;
+  bf16 *map_wkv = nullptr, *map_wo = nullptr, *map_w1 = nullptr, *map_w2 = nullptr;
+  float *map_bkv = nullptr, *map_bo = nullptr, *map_lng = nullptr, *map_lnb = nullptr, *map_b1 = nullptr,
+        *map_b2 = nullptr;
+  HeadWeights hw;
+
+  // activations
+  int mb_text = 0, mb_vis = 0;  // micro-batch capacities the arenas are sized for
+  Arena at, av;
+  bf16* im2col = nullptr;
+  uint8_t* key_valid = nullptr;
+  bf16 *map_kv = nullptr, *map_att = nullptr, *map_h = nullptr, *map_ff = nullptr;
+  float* map_y = nullptr;
+  int64_t cap_B = 0;
+  float *pooled_t = nullptr, *pooled_v = nullptr, *feat_t = nullptr, *feat_v = nullptr;
+  int last_B = 0, last_text_rows = 0, last_vis_rows = 0;
+  // host-call staging
+  int64_t host_cap = 0;
+  int64_t* d_ids = nullptr;
+  int64_t* d_mask = nullptr;
+  float *d_px = nullptr, *d_tp = nullptr, *d_ip = nullptr, *d_logits = nullptr, *d_probs = nullptr;
+  int host_S = 0;
+
+  cudaStream_t s_text = nullptr, s_vis = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_text = nullptr, ev_vis = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
+  // options
+  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 128, opt_debug_feats = 0;
+  LaunchStats stats;
+};
+typedef mmcm_handle_s Eng;
+
+template <typename T>
+static int dalloc(Eng* e, T** out, int64_t count) {
+  void* p = nullptr;
+  if (count <= 0) count = 1;
+  cudaError_t err = cudaMalloc(&p, (size_t)count * sizeof(T));
+  if (err != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc(%lld bytes) failed: %s", (long long)(count * sizeof(T)),
+                                      cudaGetErrorString(err));
+  e->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return MMCM_OK;
+}
+static void dfree(Eng* e, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < e->allocs.size(); ++i)
+    if (e->allocs[i] == p) {
+      e->allocs[i] = e->allocs.back();
+      e->allocs.pop_back();
+      break;
+    }
+  cudaFree(p);
+}
+
+static void reg(Eng* e, const std::string& key, int64_t numel, void* dst, int kind, float scale = 1.0f) {
+  Slot& s = e->slots[key];
+  s.numel = numel;
+  s.parts.push_back(Part{0, 1, numel, numel, dst, numel, kind, scale});
+}
+static void reg2d(Eng* e, const std::string& key, int64_t numel, int64_t src_off, int64_t rows, int64_t cols,
+                  int64_t src_pitch, void* dst, int64_t dst_pitch, int kind, float scale = 1.0f) {
+  Slot& s = e->slots[key];
+  s.numel = numel;
+  s.parts.push_back(Part{src_off, rows, cols, src_pitch, dst, dst_pitch, kind, scale});
+}
+
+static int setup_tower(Eng* e, TowerW& t, const std::string& prefix, int D, int H, int L, int F, int act, float eps) {
+  t.D = D; t.H = H; t.L = L; t.F = F; t.act = act; t.eps = eps;
+  if (D != H * ATT_DH) return fail(MMCM_EINVAL, "tower %s: hidden %d != heads %d * 64", prefix.c_str(), D, H);
+  if (D % 128 != 0 || F % 128 != 0) return fail(MMCM_EINVAL, "tower %s: hidden/ffn must be multiples of 128", prefix.c_str());
+  t.layers.resize(L);
+  const float qs = 1.0f / sqrtf((float)ATT_DH);  // 0.125: exact power of two, folding it into Wq/bq is lossless
+  for (int i = 0; i < L; ++i) {
+    LayerW& w = t.layers[i];
+    CKR(dalloc(e, &w.wqkv, (int64_t)3 * D * D));
+    CKR(dalloc(e, &w.bqkv, 3 * D));
+    CKR(dalloc(e, &w.wo, (int64_t)D * D));
+    CKR(dalloc(e, &w.bo, D));
+    CKR(dalloc(e, &w.w1, (int64_t)F * D));
+    CKR(dalloc(e, &w.b1, F));
+    CKR(dalloc(e, &w.w2, (int64_t)D * F));
+    CKR(dalloc(e, &w.b2, D));
+    CKR(dalloc(e, &w.ln1g, D)); CKR(dalloc(e, &w.ln1b, D));
+    CKR(dalloc(e, &w.ln2g, D)); CKR(dalloc(e, &w.ln2b, D));
+    const std::string p = prefix + "encoder.layers." + std::to_string(i) + ".";
+    const int64_t dd = (int64_t)D * D;
+    reg(e, p + "self_attn.q_proj.weight", dd, w.wqkv, 1, qs);
+    reg(e, p + "self_attn.k_proj.weight", dd, w.wqkv + dd, 1);
+    reg(e, p + "self_attn.v_proj.weight", dd, w.wqkv + 2 * dd, 1);
+    reg(e, p + "self_attn.q_proj.bias", D, w.bqkv, 0, qs);
+    reg(e, p + "self_attn.k_proj.bias", D, w.bqkv + D, 0);
+    reg(e, p + "self_attn.v_proj.bias", D, w.bqkv + 2 * D, 0);
+    reg(e, p + "self_attn.out_proj.weight", dd, w.wo, 1);
+    reg(e, p + "self_attn.out_proj.bias", D, w.bo, 0);
+    reg(e, p + "layer_norm1.weight", D, w.ln1g, 0);
+    reg(e, p + "layer_norm1.bias", D, w.ln1b, 0);
+    reg(e, p + "layer_norm2.weight", D, w.ln2g, 0);
+    reg(e, p + "layer_norm2.bias", D, w.ln2b, 0);
+    reg(e, p + "mlp.fc1.weight", (int64_t)F * D, w.w1, 1);
+    reg(e, p + "mlp.fc1.bias", F, w.b1, 0);
+    reg(e, p + "mlp.fc2.weight", (int64_t)D * F, w.w2, 1);
+    reg(e, p + "mlp.fc2.bias", D, w.b2, 0);
+  }
+  return MMCM_OK;
+}
+
+static int setup_weights(Eng* e) {
+  const mmcm_config& c = e->cfg;
+  const bool clip = c.backend == MMCM_BACKEND_CLIP;
+  const bool fusion = c.head == MMCM_HEAD_FUSION;
+  const std::string tp = fusion ? "backbone.text_model." : "tower_txt.text_model.";
+  const std::string vp = fusion ? "backbone.vision_model." : "tower_img.vision_model.";
+  CKR(setup_tower(e, e->text, tp, c.text_hidden, c.text_heads, c.text_layers, c.text_ffn, c.text_act, c.text_eps));
+  CKR(setup_tower(e, e->vis, vp, c.vis_hidden, c.vis_heads, c.vis_layers, c.vis_ffn, c.vis_act, c.vis_eps));
+  const int Dt = c.text_hidden, Dv = c.vis_hidden;
+  // text embeddings + final norm
+  CKR(dalloc(e, &e->tok_emb, (int64_t)c.vocab * Dt));
+  CKR(dalloc(e, &e->tpos_emb, (int64_t)c.max_pos * Dt));
+  CKR(dalloc(e, &e->tfin_g, Dt)); CKR(dalloc(e, &e->tfin_b, Dt));
+  reg(e, tp + "embeddings.token_embedding.weight", (int64_t)c.vocab * Dt, e->tok_emb, 0);
+  reg(e, tp + "embeddings.position_embedding.weight", (int64_t)c.max_pos * Dt, e->tpos_emb, 0);
+  reg(e, tp + "final_layer_norm.weight", Dt, e->tfin_g, 0);
+  reg(e, tp + "final_layer_norm.bias", Dt, e->tfin_b, 0);
+  // vision embeddings + norms
+  const int G = c.image / c.patch, P = G * G, Kp = 3 * c.patch * c.patch;
+  const int Tv = P + (clip ? 1 : 0);
+  if (Kp % 64 != 0) return fail(MMCM_EINVAL, "patch %d: 3*patch^2 must be a multiple of 64", c.patch);
+  CKR(dalloc(e, &e->wpatch, (int64_t)Dv * Kp));
+  CKR(dalloc(e, &e->vpos_emb, (int64_t)Tv * Dv));
+  CKR(dalloc(e, &e->post_g, Dv)); CKR(dalloc(e, &e->post_b, Dv));
+  reg(e, vp + "embeddings.patch_embedding.weight", (int64_t)Dv * Kp, e->wpatch, 1);
+  reg(e, vp + "embeddings.position_embedding.weight", (int64_t)Tv * Dv, e->vpos_emb, 0);
+  reg(e, vp + "post_layernorm.weight", Dv, e->post_g, 0);
+  reg(e, vp + "post_layernorm.bias", Dv, e->post_b, 0);
+  if (clip) {
+    CKR(dalloc(e, &e->cls_emb, Dv));
+    CKR(dalloc(e, &e->pre_g, Dv)); CKR(dalloc(e, &e->pre_b, Dv));
+    reg(e, vp + "embeddings.class_embedding", Dv, e->cls_emb, 0);
+    reg(e, vp + "pre_layrnorm.weight", Dv, e->pre_g, 0);
+    reg(e, vp + "pre_layrnorm.bias", Dv, e->pre_b, 0);
+  } else {
+    const int F = c.vis_ffn;
+    const int64_t dd = (int64_t)Dv * Dv;
+    CKR(dalloc(e, &e->bpatch, Dv));
+    reg(e, vp + "embeddings.patch_embedding.bias", Dv, e->bpatch, 0);
+    CKR(dalloc(e, &e->thead_w, (int64_t)c.proj_dim * Dt)); CKR(dalloc(e, &e->thead_b, c.proj_dim));
+    reg(e, tp + "head.weight", (int64_t)c.proj_dim * Dt, e->thead_w, 0);
+    reg(e, tp + "head.bias", c.proj_dim, e->thead_b, 0);
+    // MAP head (HF siglip :586-649): packed in_proj -> fp32 q rows (probe projection) + bf16 K|V rows
+    CKR(dalloc(e, &e->map_probe, Dv));
+    CKR(dalloc(e, &e->map_inw, dd)); CKR(dalloc(e, &e->map_inb, Dv)); CKR(dalloc(e, &e->map_q, Dv));
+    CKR(dalloc(e, &e->map_wkv, 2 * dd)); CKR(dalloc(e, &e->map_bkv, 2 * Dv));
+    CKR(dalloc(e, &e->map_wo, dd)); CKR(dalloc(e, &e->map_bo, Dv));
+    CKR(dalloc(e, &e->map_lng, Dv)); CKR(dalloc(e, &e->map_lnb, Dv));
+    CKR(dalloc(e, &e->map_w1, (int64_t)F * Dv)); CKR(dalloc(e, &e->map_b1, F));
+    CKR(dalloc(e, &e->map_w2, (int64_t)Dv * F)); CKR(dalloc(e, &e->map_b2, Dv));
+    const std::string h = vp + "head.";
+    reg(e, h + "probe", Dv, e->map_probe, 0);
+    reg2d(e, h + "attention.in_proj_weight", 3 * dd, 0, 1, dd, dd, e->map_inw, dd, 0);
+    reg2d(e, h + "attention.in_proj_weight", 3 * dd, dd, 1, 2 * dd, 2 * dd, e->map_wkv, 2 * dd, 1);
+    reg2d(e, h + "attention.in_proj_bias", 3 * Dv, 0, 1, Dv, Dv, e->map_inb, Dv, 0);
+    reg2d(e, h + "attention.in_proj_bias", 3 * Dv, Dv, 1, 2 * Dv, 2 * Dv, e->map_bkv, 2 * Dv, 0);
+    reg(e, h + "attention.out_proj.weight", dd, e->map_wo, 1);
+    reg(e, h + "attention.out_proj.bias", Dv, e->map_bo, 0);
+    reg(e, h + "layernorm.weight", Dv, e->map_lng, 0);
+    reg(e, h + "layernorm.bias", Dv, e->map_lnb, 0);
+    reg(e, h + "mlp.fc1.weight", (int64_t)F * Dv, e->map_w1, 1);
+    reg(e, h + "mlp.fc1.bias", F, e->map_b1, 0);
+    reg(e, h + "mlp.fc2.weight", (int64_t)Dv * F, e->map_w2, 1);
+    reg(e, h + "mlp.fc2.bias", Dv, e->map_b2, 0);
+  }
+  // ---- heads (fp32)
+  HeadWeights& w = e->hw;
+  memset(&w, 0, sizeof(w));
+  const int fd = c.fusion_dim, C = c.num_outputs;
+  w.head = c.head; w.backend = c.backend; w.fd = fd; w.n_out = C; w.hh = c.head_hidden_dim;
+  w.dt = clip ? Dt : c.proj_dim;  // siglip: the text head maps Dt -> proj_dim (== Dt for every released SigLIP)
+  w.dv = Dv;
+  if (!clip && c.proj_dim != Dt) return fail(MMCM_EINVAL, "siglip: projection_size %d != text hidden %d", c.proj_dim, Dt);
+  auto f32 = [&](const std::string& key, int64_t n, const float** field) -> int {
+    float* p = nullptr;
+    CKR(dalloc(e, &p, n));
+    reg(e, key, n, p, 0);
+    *field = p;
+    return MMCM_OK;
+  };
+  int din_t, din_v;
+  if (fusion) {
+    if (clip) {
+      w.dp = c.proj_dim;
+      CKR(f32("backbone.text_projection.weight", (int64_t)c.proj_dim * Dt, &w.text_proj));
+      CKR(f32("backbone.visual_projection.weight", (int64_t)c.proj_dim * Dv, &w.vis_proj));
+      din_t = din_v = c.proj_dim;
+    } else {
+      w.dp = c.proj_dim;
+      w.text_head_w = e->thead_w; w.text_head_b = e->thead_b;
+      din_t = c.proj_dim; din_v = Dv;
+      if (din_t != din_v) return fail(MMCM_EINVAL, "siglip fusion: text %d and vision %d feature widths differ", din_t, din_v);
+    }
+  } else {
+    if (!clip) return fail(MMCM_EINVAL, "MultiTaskClassifier supports the clip backend only "
+                                        "(the reference asserts for AutoModel backends, multitask.py:81-88)");
+    w.dp = 0;
+    din_t = Dt; din_v = Dv;
+  }
+  if (din_t > HEAD_MAXD || din_v > HEAD_MAXD || fd > HEAD_MAXD || fd % 4 != 0 || din_t % 4 != 0 || din_v % 4 != 0 ||
+      (clip && fusion && c.proj_dim > fd))
+    return fail(MMCM_EINVAL, "head: unsupported widths (text %d vision %d fusion %d)", din_t, din_v, fd);
+  if (C > fd) return fail(MMCM_EINVAL, "head: num_outputs %d > fusion_dim %d", C, fd);
+  CKR(f32("proj_t.weight", (int64_t)fd * din_t, &w.proj_t_w)); CKR(f32("proj_t.bias", fd, &w.proj_t_b));
+  CKR(f32("proj_i.weight", (int64_t)fd * din_v, &w.proj_i_w)); CKR(f32("proj_i.bias", fd, &w.proj_i_b));
+  CKR(f32("g_t.weight", (int64_t)fd * fd, &w.g_t_w)); CKR(f32("g_t.bias", fd, &w.g_t_b));
+  CKR(f32("g_i.weight", (int64_t)fd * fd, &w.g_i_w)); CKR(f32("g_i.bias", fd, &w.g_i_b));
+  {  // gate.weight [fd, 2fd+2] -> dense [fd, 2fd] + the two presence columns [fd, 2]
+    float *gw = nullptr, *gp = nullptr;
+    CKR(dalloc(e, &gw, (int64_t)fd * 2 * fd));
+    CKR(dalloc(e, &gp, (int64_t)fd * 2));
+    const int64_t n = (int64_t)fd * (2 * fd + 2);
+    reg2d(e, "gate.weight", n, 0, fd, 2 * fd, 2 * fd + 2, gw, 2 * fd, 0);
+    reg2d(e, "gate.weight", n, 2 * fd, fd, 2, 2 * fd + 2, gp, 2, 0);
+    w.gate_w = gw; w.gate_wp = gp;
+    CKR(f32("gate.bias", fd, &w.gate_b));
+  }
+  if (fusion) {
+    CKR(f32("ln_fused.weight", fd, &w.ln_fused_g)); CKR(f32("ln_fused.bias", fd, &w.ln_fused_b));
+    CKR(f32("cls.0.weight", 5 * fd, &w.cls0_g)); CKR(f32("cls.0.bias", 5 * fd, &w.cls0_b));
+    CKR(f32("cls.1.weight", (int64_t)fd * 5 * fd, &w.cls1_w)); CKR(f32("cls.1.bias", fd, &w.cls1_b));
+    CKR(f32("cls.4.weight", (int64_t)C * fd, &w.cls4_w)); CKR(f32("cls.4.bias", C, &w.cls4_b));
+  } else {
+    CKR(f32("shared_head.1.weight", (int64_t)fd * fd, &w.shared_w)); CKR(f32("shared_head.1.bias", fd, &w.shared_b));
+    const int hh = c.head_hidden_dim;
+    if (hh > 0) {
+      if (hh > fd || hh % 4 != 0) return fail(MMCM_EINVAL, "mtl: head_hidden_dim %d must be <= fusion_dim and %% 4 == 0", hh);
+      float *h0w, *h0b, *h3w, *h3b;
+      CKR(dalloc(e, &h0w, (int64_t)C * hh * fd)); CKR(dalloc(e, &h0b, (int64_t)C * hh));
+      CKR(dalloc(e, &h3w, (int64_t)C * hh)); CKR(dalloc(e, &h3b, C));
+      for (int j = 0; j < C; ++j) {
+        const std::string p = "heads." + std::to_string(j) + ".";
+        reg(e, p + "0.weight", (int64_t)hh * fd, h0w + (int64_t)j * hh * fd, 0);
+        reg(e, p + "0.bias", hh, h0b + (int64_t)j * hh, 0);
+        reg(e, p + "3.weight", hh, h3w + (int64_t)j * hh, 0);
+        reg(e, p + "3.bias", 1, h3b + j, 0);
+      }
+      w.h0_w = h0w; w.h0_b = h0b; w.h3_w = h3w; w.h3_b = h3b;
+    } else {
+      float *h3w, *h3b;
+      CKR(dalloc(e, &h3w, (int64_t)C * fd)); CKR(dalloc(e, &h3b, C));
+      for (int j = 0; j < C; ++j) {
+        const std::string p = "heads." + std::to_string(j) + ".";
+        reg(e, p + "weight", fd, h3w + (int64_t)j * fd, 0);
+        reg(e, p + "bias", 1, h3b + j, 0);
+      }
+      w.h3_w = h3w; w.h3_b = h3b;
+    }
+  }
+  return MMCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ arenas
+static void free_arena(Eng* e, Arena& a) {
+  dfree(e, a.x); dfree(e, a.h); dfree(e, a.qkv); dfree(e, a.att); dfree(e, a.ff); dfree(e, a.pool_row);
+  a = Arena();
+}
+static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) {
+  a.rows = rows;
+  CKR(dalloc(e, &a.x, rows * t.D));
+  CKR(dalloc(e, &a.h, rows * t.D));
+  CKR(dalloc(e, &a.qkv, rows * 3 * t.D));
+  CKR(dalloc(e, &a.att, rows * t.D));
+  CKR(dalloc(e, &a.ff, rows * t.F));
+  CKR(dalloc(e, &a.pool_row, mb));
+  return MMCM_OK;
+}
+
+static int vis_tokens(const mmcm_config& c) {
+  const int G = c.image / c.patch;
+  return G * G + (c.backend == MMCM_BACKEND_CLIP ? 1 : 0);
+}
+
+static int ensure_arenas(Eng* e, int mb) {
+  const mmcm_config& c = e->cfg;
+  if (mb <= e->mb_text && mb <= e->mb_vis) return MMCM_OK;
+  CK(cudaDeviceSynchronize());
+  free_arena(e, e->at);
+  free_arena(e, e->av);
+  dfree(e, e->im2col); dfree(e, e->key_valid);
+  dfree(e, e->map_kv); dfree(e, e->map_att); dfree(e, e->map_h); dfree(e, e->map_ff); dfree(e, e->map_y);
+  e->im2col = nullptr; e->key_valid = nullptr;
+  e->map_kv = e->map_att = e->map_h = e->map_ff = nullptr; e->map_y = nullptr;
+  const int Tv = vis_tokens(c);
+  const int G = c.image / c.patch, P = G * G, Kp = 3 * c.patch * c.patch;
+  CKR(alloc_arena(e, e->at, e->text, (int64_t)mb * c.max_pos, mb));
+  CKR(alloc_arena(e, e->av, e->vis, (int64_t)mb * Tv, mb));
+  CKR(dalloc(e, &e->im2col, (int64_t)mb * P * Kp));
+  CKR(dalloc(e, &e->key_valid, (int64_t)mb * c.max_pos));
+  if (c.backend == MMCM_BACKEND_SIGLIP) {
+    const int D = c.vis_hidden;
+    CKR(dalloc(e, &e->map_kv, (int64_t)mb * Tv * 2 * D));
+    CKR(dalloc(e, &e->map_att, (int64_t)mb * D));
+    CKR(dalloc(e, &e->map_h, (int64_t)mb * D));
+    CKR(dalloc(e, &e->map_ff, (int64_t)mb * c.vis_ffn));
+    CKR(dalloc(e, &e->map_y, (int64_t)mb * D));
+  }
+  e->mb_text = e->mb_vis = mb;
+  return MMCM_OK;
+}
+
+static int ensure_batch(Eng* e, int64_t B) {
+  if (B <= e->cap_B) return MMCM_OK;
+  CK(cudaDeviceSynchronize());
+  dfree(e, e->pooled_t); dfree(e, e->pooled_v); dfree(e, e->feat_t); dfree(e, e->feat_v);
+  int64_t cap = e->cap_B ? e->cap_B : 64;
+  while (cap < B) cap *= 2;
+  CKR(dalloc(e, &e->pooled_t, cap * e->cfg.text_hidden));
+  CKR(dalloc(e, &e->pooled_v, cap * e->cfg.vis_hidden));
+  CKR(dalloc(e, &e->feat_t, cap * HEAD_MAXD));
+  CKR(dalloc(e, &e->feat_v, cap * HEAD_MAXD));
+  e->cap_B = cap;
+  return MMCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ towers
+static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T, const uint8_t* kvalid, int causal,
+                      cudaStream_t st) {
+  LaunchStats* S = &e->stats;
+  const int D = t.D, F = t.F, impl = e->opt_gemm_impl;
+  for (int i = 0; i < t.L; ++i) {
+    const LayerW& w = t.layers[i];
+    // h = LN1(x)                                               HF clip :372
+    CKR(launch_layernorm(a.x, w.ln1g, w.ln1b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    // qkv = h @ [Wq*s | Wk | Wv]^T + [bq*s | bk | bv]          HF clip :313-319
+    EpiParams ep{};
+    ep.bias = w.bqkv; ep.out = a.qkv; ep.ldo = 3 * D;
+    CKR(launch_gemm(a.h, w.wqkv, rows, 3 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
+    // att = softmax(q k^T + mask) v                            HF clip :321-332
+    CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S));
+    // x = x + att @ Wo^T + bo                                  HF clip :334, :379
+    ep = EpiParams{};
+    ep.bias = w.bo; ep.out = a.x; ep.resid = a.x; ep.ldo = D;
+    CKR(launch_gemm(a.att, w.wo, rows, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
+    // h = LN2(x); ff = act(h @ W1^T + b1); x = x + ff @ W2^T + b2      HF clip :381-384, :347-351
+    CKR(launch_layernorm(a.x, w.ln2g, w.ln2b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    ep = EpiParams{};
+    ep.bias = w.b1; ep.out = a.ff; ep.ldo = F; ep.act = t.act;
+    CKR(launch_gemm(a.h, w.w1, rows, F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
+    ep = EpiParams{};
+    ep.bias = w.b2; ep.out = a.x; ep.resid = a.x; ep.ldo = D;
+    CKR(launch_gemm(a.ff, w.w2, rows, D, F, EPI_BIAS_RESID_F32, ep, impl, st, S));
+  }
+  return MMCM_OK;
+}
+
+static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int S, float* pooled, cudaStream_t st) {
+  const mmcm_config& c = e->cfg;
+  const TowerW& t = e->text;
+  Arena& a = e->at;
+  const int rows = n * S;
+  const bool clip = c.backend == MMCM_BACKEND_CLIP;
+  const int blocks = (rows + 7) / 8;
+  const int eos = clip ? c.eos_id : -1;
+  if (t.D == 512)
+    text_embed_kernel<512><<<blocks, 256, 0, st>>>(ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                                                   a.pool_row, e->key_valid);
+  else if (t.D == 768)
+    text_embed_kernel<768><<<blocks, 256, 0, st>>>(ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                                                   a.pool_row, e->key_valid);
+  else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
+  CK(cudaGetLastError());
+  e->stats.launches++;
+  CKR(run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st));
+  // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
+  CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
+  e->last_text_rows = rows;
+  return MMCM_OK;
+}
+
+static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_t st) {
+  const mmcm_config& c = e->cfg;
+  const TowerW& t = e->vis;
+  Arena& a = e->av;
+  LaunchStats* S = &e->stats;
+  const bool clip = c.backend == MMCM_BACKEND_CLIP;
+  const int G = c.image / c.patch, P = G * G, Kp = 3 * c.patch * c.patch, T = vis_tokens(c), D = t.D;
+  const int rows = n * T;
+  // patch embedding = im2col + GEMM, position embedding (and conv bias) fused into the epilogue   HF clip :202-218
+  {
+    const int64_t chunks = (int64_t)n * P * (Kp / 8);
+    const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
+    im2col_kernel<<<blocks, 256, 0, st>>>(px, e->im2col, n, c.image, c.patch);
+    CK(cudaGetLastError());
+    S->launches++;
+  }
+  EpiParams ep{};
+  ep.bias = e->bpatch; ep.out = a.x; ep.pos = e->vpos_emb; ep.ldo = D; ep.P = P; ep.T = T;
+  CKR(launch_gemm(e->im2col, e->wpatch, n * P, D, Kp, EPI_PATCH_F32, ep, e->opt_gemm_impl, st, S));
+  if (clip) {
+    cls_rows_kernel<<<(n * D + 255) / 256, 256, 0, st>>>(e->cls_emb, e->vpos_emb, a.x, n, T, D);
+    CK(cudaGetLastError());
+    S->launches++;
+    CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
+  }
+  CKR(run_layers(e, t, a, rows, n, T, nullptr, 0, st));
+  if (clip) {
+    fill_pool_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.pool_row, n, T, 0);
+    CK(cudaGetLastError());
+    S->launches++;
+    CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S));
+  } else {
+    // post_layernorm over all tokens, then the MAP head   HF siglip :617-649
+    const int impl = e->opt_gemm_impl;
+    CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    ep = EpiParams{};
+    ep.bias = e->map_bkv; ep.out = e->map_kv; ep.ldo = 2 * D;
+    CKR(launch_gemm(a.h, e->map_wkv, rows, 2 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
+    if (T > MAP_MAXT) return fail(MMCM_EINVAL, "MAP head: %d tokens > %d", T, MAP_MAXT);
+    map_attention_kernel<<<dim3(t.H, n), 128, 0, st>>>(e->map_kv, e->map_q, e->map_att, T, D);
+    CK(cudaGetLastError());
+    S->launches++;
+    ep = EpiParams{};
+    ep.bias = e->map_bo; ep.out = e->map_y; ep.ldo = D;
+    CKR(launch_gemm(e->map_att, e->map_wo, n, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
+    CKR(launch_layernorm(e->map_y, e->map_lng, e->map_lnb, t.eps, n, D, nullptr, e->map_h, nullptr, st, S));
+    ep = EpiParams{};
+    ep.bias = e->map_b1; ep.out = e->map_ff; ep.ldo = t.F; ep.act = t.act;
+    CKR(launch_gemm(e->map_h, e->map_w1, n, t.F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
+    ep = EpiParams{};
+    ep.bias = e->map_b2; ep.out = pooled; ep.resid = e->map_y; ep.ldo = D;
+    CKR(launch_gemm(e->map_ff, e->map_w2, n, D, t.F, EPI_BIAS_RESID_F32, ep, impl, st, S));
+  }
+  e->last_vis_rows = rows;
+  return MMCM_OK;
+}
+
+static int run_head(Eng* e, const float* tp, const float* ip, int B, float* logits, float* probs, cudaStream_t st) {
+  static AttrOnce once;
+  const int smem = head_smem_bytes(e->cfg.fusion_dim);
+  if (once.need()) CK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (smem > 200 * 1024) return fail(MMCM_EINVAL, "head: fusion_dim %d needs too much shared memory", e->cfg.fusion_dim);
+  const bool dbg = e->opt_debug_feats && e->cfg.head == MMCM_HEAD_FUSION;
+  head_kernel<<<(B + HEAD_SB - 1) / HEAD_SB, HEAD_THREADS, smem, st>>>(
+      e->hw, e->pooled_t, e->pooled_v, tp, ip, B, logits, probs, dbg ? e->feat_t : nullptr, dbg ? e->feat_v : nullptr);
+  CK(cudaGetLastError());
+  e->stats.launches++;
+  return MMCM_OK;
+}
+
+static void clear_gemm_events(LaunchStats& s) {
+  for (auto& p : s.gemm_events) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  s.gemm_events.clear();
+  s.gemm_flops = 0;
+}
+
+static int check_forward_args(Eng* e, const void* ids, const void* px, const void* tp, const void* ip, int B, int S,
+                              const void* logits) {
+  if (!e) return fail(MMCM_EINVAL, "null handle");
+  if (!e->finalized) return fail(MMCM_ESTATE, "weights are not finalized (call mmcm_finalize_weights)");
+  if (B < 0 || S <= 0) return fail(MMCM_EINVAL, "bad batch %d or sequence length %d", B, S);
+  if (S > e->cfg.max_pos)  // mirrors HF/models/clip/modeling_clip.py:243-247 (siglip :211-215)
+    return fail(MMCM_EINVAL,
+                "Sequence length must be less than max_position_embeddings (got `sequence length`: %d and "
+                "max_position_embeddings: %d", S, e->cfg.max_pos);
+  if (B > 0 && (!ids || !px || !tp || !ip || !logits)) return fail(MMCM_EINVAL, "null input/output pointer");
+  return MMCM_OK;
+}
+
+static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const float* px, const float* tp,
+                          const float* ip, int B, int S, float* logits, float* probs, cudaStream_t st) {
+  const mmcm_config& c = e->cfg;
+  e->stats.launches = 0;
+  clear_gemm_events(e->stats);
+  if (B == 0) return MMCM_OK;
+  int mb = e->opt_micro_batch;
+  if (mb > B) mb = B;
+  CKR(ensure_arenas(e, mb));
+  CKR(ensure_batch(e, B));
+  const bool two = e->opt_streams >= 2;
+  cudaStream_t stx = two ? e->s_text : st, svx = two ? e->s_vis : st;
+  if (two) {
+    CK(cudaEventRecord(e->ev_fork, st));
+    CK(cudaStreamWaitEvent(stx, e->ev_fork, 0));
+    CK(cudaStreamWaitEvent(svx, e->ev_fork, 0));
+  }
+  const int64_t px_per = (int64_t)3 * c.image * c.image;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int n = (B - b0 < mb) ? (B - b0) : mb;
+    CKR(run_text(e, ids + (int64_t)b0 * S, mask ? mask + (int64_t)b0 * S : nullptr, n, S,
+                 e->pooled_t + (int64_t)b0 * c.text_hidden, stx));
+    CKR(run_vision(e, px + b0 * px_per, n, e->pooled_v + (int64_t)b0 * c.vis_hidden, svx));
+  }
+  if (two) {
+    CK(cudaEventRecord(e->ev_text, stx));
+    CK(cudaEventRecord(e->ev_vis, svx));
+    CK(cudaStreamWaitEvent(st, e->ev_text, 0));
+    CK(cudaStreamWaitEvent(st, e->ev_vis, 0));
+  }
+  CKR(run_head(e, tp, ip, B, logits, probs, st));
+  e->last_B = B;
+  return MMCM_OK;
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* mmcm_last_error(void) { return g_err; }
+const char* mmcm_version(void) { return "mmcm-b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
+
+int mmcm_create(const mmcm_config* cfg, int device, mmcm_handle* out) {
+  if (!cfg || !out) return fail(MMCM_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return fail(MMCM_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(MMCM_EINVAL, "device %d out of range [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MMCM_ECUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  if (cfg->backend != MMCM_BACKEND_CLIP && cfg->backend != MMCM_BACKEND_SIGLIP) return fail(MMCM_EINVAL, "bad backend");
+  if (cfg->head != MMCM_HEAD_FUSION && cfg->head != MMCM_HEAD_MTL) return fail(MMCM_EINVAL, "bad head");
+  if (cfg->image <= 0 || cfg->patch <= 0 || cfg->image % cfg->patch != 0 || cfg->patch % 8 != 0)
+    return fail(MMCM_EINVAL, "bad image/patch %d/%d", cfg->image, cfg->patch);
+  if (cfg->num_outputs <= 0 || cfg->max_pos <= 0 || cfg->vocab <= 0) return fail(MMCM_EINVAL, "bad sizes");
+  if (cfg->max_pos > 256 || vis_tokens(*cfg) > 256) return fail(MMCM_EINVAL, "sequences longer than 256 tokens are unsupported");
+  CKR(ensure_driver());
+  Eng* e = new Eng();
+  e->cfg = *cfg;
+  e->device = device;
+  int r = setup_weights(e);
+  if (r == MMCM_OK) {
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->s_text, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->s_vis, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_text, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_vis, cudaEventDisableTiming);
+    if (ce != cudaSuccess) r = fail(MMCM_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
+  }
+  if (r != MMCM_OK) {
+    mmcm_destroy(e);
+    return r;
+  }
+  *out = e;
+  return MMCM_OK;
+}
+
+int mmcm_destroy(mmcm_handle h) {
+  if (!h) return MMCM_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  clear_gemm_events(h->stats);
+  for (void* p : h->allocs) cudaFree(p);
+  {  // cached tensor maps may point into freed memory that a later allocation re-uses with another shape
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_tmaps.clear();
+  }
+  if (h->s_text) cudaStreamDestroy(h->s_text);
+  if (h->s_vis) cudaStreamDestroy(h->s_vis);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_text) cudaEventDestroy(h->ev_text);
+  if (h->ev_vis) cudaEventDestroy(h->ev_vis);
+  for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
+  delete h;
+  return MMCM_OK;
+}
+
+static bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+int mmcm_load_weight(mmcm_handle h, const char* key, const float* src, int64_t numel) {
+  if (!h || !key || !src) return fail(MMCM_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  const std::string k(key);
+  auto it = h->slots.find(k);
+  if (it == h->slots.end()) {
+    // tensors of the reference's state dict that the scoring path never reads
+    if (ends_with(k, "logit_scale") || ends_with(k, "logit_bias") || k == "pos_weight" || k == "log_vars" ||
+        ends_with(k, "position_ids") || k.rfind("criterion.", 0) == 0)
+      return MMCM_OK;
+    return fail(MMCM_EINVAL, "unexpected key '%s' for this model configuration", key);
+  }
+  Slot& s = it->second;
+  if (numel != s.numel)
+    return fail(MMCM_EINVAL, "size mismatch for '%s': got %lld elements, expected %lld", key, (long long)numel,
+                (long long)s.numel);
+  // stage on the device (src may be host or device memory), then scatter/convert the pieces
+  const float* dsrc = src;
+  float* stage = nullptr;
+  cudaPointerAttributes attr;
+  cudaError_t pe = cudaPointerGetAttributes(&attr, src);
+  const bool on_device = (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged));
+  if (pe != cudaSuccess) cudaGetLastError();
+  if (!on_device) {
+    cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&stage), (size_t)numel * 4);
+    if (ce != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc staging for '%s' failed: %s", key, cudaGetErrorString(ce));
+    ce = cudaMemcpy(stage, src, (size_t)numel * 4, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      cudaFree(stage);
+      return fail(MMCM_ECUDA, "H2D copy of '%s' failed: %s", key, cudaGetErrorString(ce));
+    }
+    dsrc = stage;
+  }
+  for (const Part& p : s.parts) {
+    const int64_t total = p.rows * p.cols;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    copy2d_kernel<<<blocks, 256>>>(dsrc + p.src_off, p.dst, p.rows, p.cols, p.src_pitch, p.dst_pitch, p.kind, p.scale);
+  }
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (stage) cudaFree(stage);
+  if (ce != cudaSuccess) return fail(MMCM_ECUDA, "weight repack of '%s' failed: %s", key, cudaGetErrorString(ce));
+  s.loaded = true;
+  h->finalized = false;
+  return MMCM_OK;
+}
+
+int mmcm_finalize_weights(mmcm_handle h) {
+  if (!h) return fail(MMCM_EINVAL, "null handle");
+  CK(cudaSetDevice(h->device));
+  int missing = 0;
+  std::string first;
+  for (auto& kv : h->slots)
+    if (!kv.second.loaded) {
+      if (!missing || kv.first < first) first = kv.first;
+      ++missing;
+    }
+  if (missing) return fail(MMCM_ESTATE, "%d weight tensor(s) missing, e.g. '%s'", missing, first.c_str());
+  if (h->cfg.backend == MMCM_BACKEND_SIGLIP) {
+    const int D = h->cfg.vis_hidden;
+    probe_query_kernel<<<(D + 7) / 8, 256>>>(h->map_inw, h->map_inb, h->map_probe, h->map_q, D, 1.0f / sqrtf((float)ATT_DH));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  }
+  h->finalized = true;
+  return MMCM_OK;
+}
+
+int mmcm_forward(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask, const float* pixel_values,
+                 const float* text_present, const float* image_present, int32_t B, int32_t S, float* logits_out,
+                 float* probs_out, void* stream) {
+  CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
+  CK(cudaSetDevice(h->device));
+  return forward_device(h, input_ids, attention_mask, pixel_values, text_present, image_present, B, S, logits_out,
+                        probs_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                      const float* pixel_values, const float* text_present, const float* image_present, int32_t B,
+                      int32_t S, float* logits_out, float* probs_out, void* stream) {
+  CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
+  CK(cudaSetDevice(h->device));
+  Eng* e = h;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B == 0) return MMCM_OK;
+  const mmcm_config& c = e->cfg;
+  const int64_t px_per = (int64_t)3 * c.image * c.image;
+  const int C = c.num_outputs;
+  if (B > e->host_cap || S > e->host_S) {
+    CK(cudaDeviceSynchronize());
+    dfree(e, e->d_ids); dfree(e, e->d_mask); dfree(e, e->d_px); dfree(e, e->d_tp); dfree(e, e->d_ip);
+    dfree(e, e->d_logits); dfree(e, e->d_probs);
+    int64_t cap = e->host_cap ? e->host_cap : 64;
+    while (cap < B) cap *= 2;
+    const int Sc = c.max_pos;
+    CKR(dalloc(e, &e->d_ids, cap * Sc)); CKR(dalloc(e, &e->d_mask, cap * Sc));
+    CKR(dalloc(e, &e->d_px, cap * px_per));
+    CKR(dalloc(e, &e->d_tp, cap)); CKR(dalloc(e, &e->d_ip, cap));
+    CKR(dalloc(e, &e->d_logits, cap * C)); CKR(dalloc(e, &e->d_probs, cap * C));
+    e->host_cap = cap; e->host_S = Sc;
+  }
+  // small inputs first, then the pixels in micro-batch chunks on the copy stream so that the H2D transfer of
+  // chunk i+1 overlaps the towers of chunk i
+  CK(cudaMemcpyAsync(e->d_ids, input_ids, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
+  if (attention_mask) CK(cudaMemcpyAsync(e->d_mask, attention_mask, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_tp, text_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_ip, image_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  int mb = e->opt_micro_batch;
+  if (mb > B) mb = B;
+  CKR(ensure_arenas(e, mb));
+  CKR(ensure_batch(e, B));
+  const int nchunks = (B + mb - 1) / mb;
+  while ((int)e->ev_chunk.size() < nchunks) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->ev_chunk.push_back(ev);
+  }
+  CK(cudaEventRecord(e->ev_fork, st));
+  CK(cudaStreamWaitEvent(e->s_copy, e->ev_fork, 0));
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int b0 = ci * mb, n = (B - b0 < mb) ? (B - b0) : mb;
+    CK(cudaMemcpyAsync(e->d_px + b0 * px_per, pixel_values + b0 * px_per, (size_t)n * px_per * 4,
+                       cudaMemcpyHostToDevice, e->s_copy));
+    CK(cudaEventRecord(e->ev_chunk[ci], e->s_copy));
+  }
+  e->stats.launches = 0;
+  clear_gemm_events(e->stats);
+  CK(cudaStreamWaitEvent(e->s_text, e->ev_fork, 0));
+  CK(cudaStreamWaitEvent(e->s_vis, e->ev_fork, 0));
+  const int64_t* dmask = attention_mask ? e->d_mask : nullptr;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int b0 = ci * mb, n = (B - b0 < mb) ? (B - b0) : mb;
+    CKR(run_text(e, e->d_ids + (int64_t)b0 * S, dmask ? dmask + (int64_t)b0 * S : nullptr, n, S,
+                 e->pooled_t + (int64_t)b0 * c.text_hidden, e->s_text));
+    CK(cudaStreamWaitEvent(e->s_vis, e->ev_chunk[ci], 0));
+    CKR(run_vision(e, e->d_px + b0 * px_per, n, e->pooled_v + (int64_t)b0 * c.vis_hidden, e->s_vis));
+  }
+  CK(cudaEventRecord(e->ev_text, e->s_text));
+  CK(cudaEventRecord(e->ev_vis, e->s_vis));
+  CK(cudaStreamWaitEvent(st, e->ev_text, 0));
+  CK(cudaStreamWaitEvent(st, e->ev_vis, 0));
+  CKR(run_head(e, e->d_tp, e->d_ip, B, e->d_logits, probs_out ? e->d_probs : nullptr, st));
+  e->last_B = B;
+  CK(cudaMemcpyAsync(logits_out, e->d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+  if (probs_out) CK(cudaMemcpyAsync(probs_out, e->d_probs, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MMCM_OK;
+}
+
+int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity, int64_t* numel_out, void* stream) {
+  if (!h || !name || !numel_out) return fail(MMCM_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  const std::string n(name);
+  const float* src = nullptr;
+  int64_t count = 0;
+  if (n == "text_pooled") { src = h->pooled_t; count = (int64_t)h->last_B * h->cfg.text_hidden; }
+  else if (n == "vision_pooled") { src = h->pooled_v; count = (int64_t)h->last_B * h->cfg.vis_hidden; }
+  else if (n == "text_hidden") { src = h->at.x; count = (int64_t)h->last_text_rows * h->cfg.text_hidden; }
+  else if (n == "vision_hidden") { src = h->av.x; count = (int64_t)h->last_vis_rows * h->cfg.vis_hidden; }
+  else if (n == "text_feat" || n == "vision_feat") {
+    if (!h->opt_debug_feats || h->cfg.head != MMCM_HEAD_FUSION)
+      return fail(MMCM_ESTATE, "stage '%s' needs option debug_feats=1 and a fusion head", name);
+    const bool t = n == "text_feat";
+    src = t ? h->feat_t : h->feat_v;
+    const int w = (h->cfg.backend == MMCM_BACKEND_CLIP) ? h->cfg.proj_dim : (t ? h->cfg.proj_dim : h->cfg.vis_hidden);
+    count = (int64_t)h->last_B * w;
+  } else return fail(MMCM_EINVAL, "unknown stage '%s'", name);
+  *numel_out = count;
+  if (!dst) return MMCM_OK;  // size query
+  if (capacity < count) return fail(MMCM_EINVAL, "stage '%s' needs %lld elements, buffer has %lld", name,
+                                    (long long)count, (long long)capacity);
+  if (count > 0 && !src) return fail(MMCM_ESTATE, "no forward has run yet");
+  if (count > 0)
+    CK(cudaMemcpyAsync(dst, src, (size_t)count * 4, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return MMCM_OK;
+}
+
+int64_t mmcm_last_launch_count(mmcm_handle h) { return h ? h->stats.launches : 0; }
+
+int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
+  if (!h) return fail(MMCM_EINVAL, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  double ms = 0;
+  for (auto& p : h->stats.gemm_events) {
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, p.first, p.second));
+    ms += t;
+  }
+  if (ms_out) *ms_out = ms;
+  if (flops_out) *flops_out = h->stats.gemm_flops;
+  if (launches_out) *launches_out = (int64_t)h->stats.gemm_events.size();
+  return MMCM_OK;
+}
+
+int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
+  if (!h || !name) return fail(MMCM_EINVAL, "null argument");
+  const std::string n(name);
+  if (n == "time_gemms") h->stats.time_gemms = value != 0;
+  else if (n == "gemm_impl") {
+    if (value != 0 && value != 1) return fail(MMCM_EINVAL, "gemm_impl must be 0 (tcgen05) or 1 (SIMT validation)");
+    h->opt_gemm_impl = (int)value;
+  } else if (n == "micro_batch") {
+    if (value < 1 || value > 65536) return fail(MMCM_EINVAL, "micro_batch out of range");
+    h->opt_micro_batch = (int)value;
+  } else if (n == "streams") {
+    if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
+    h->opt_streams = (int)value;
+  } else if (n == "debug_feats") h->opt_debug_feats = value != 0;
+  else return fail(MMCM_EINVAL, "unknown option '%s'", name);
+  return MMCM_OK;
+}
+
+// ---------------------------------------------------------------------------------- stand-alone kernels
+int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                   int32_t act, void* out, const float* resid, const float* pos, int32_t P, int32_t T, int32_t impl,
+                   void* stream) {
+  if (!A || !W || !out) return fail(MMCM_EINVAL, "null pointer");
+  if (epilogue == EPI_PATCH_F32 && (!pos || P <= 0 || T < P)) return fail(MMCM_EINVAL, "patch epilogue needs pos, P, T");
+  EpiParams ep{};
+  ep.bias = bias; ep.out = out; ep.resid = resid; ep.pos = pos; ep.ldo = N; ep.P = P; ep.T = T; ep.act = act;
+  return launch_gemm(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(W), M, N, K, epilogue, ep, impl,
+                     reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
+                   void* out_bf16, float* out_f32, void* stream) {
+  if (!x || !gamma || !beta) return fail(MMCM_EINVAL, "null pointer");
+  return launch_layernorm(x, gamma, beta, eps, rows, D, nullptr, reinterpret_cast<bf16*>(out_bf16), out_f32,
+                          reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B, int32_t T, int32_t heads, int32_t causal,
+                   void* out, void* stream) {
+  if (!qkv || !out) return fail(MMCM_EINVAL, "null pointer");
+  if (T <= 0 || heads <= 0) return fail(MMCM_EINVAL, "bad T/heads");
+  return launch_attention(reinterpret_cast<const bf16*>(qkv), key_valid, B, T, heads, causal,
+                          reinterpret_cast<bf16*>(out), reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_cast_bf16(const float* src, void* dst, int64_t n, float scale, void* stream) {
+  if (!src || !dst) return fail(MMCM_EINVAL, "null pointer");
+  if (n <= 0) return MMCM_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst),
+                                                                              (size_t)n, scale);
+  CK(cudaGetLastError());
+  return MMCM_OK;
+}
+
+}  // extern "C"

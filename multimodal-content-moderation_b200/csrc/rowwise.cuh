@@ -1,0 +1,187 @@
+// K4 / K5 / K6 and the small HBM-bound helpers: LayerNorm, embeddings, im2col, pooling-row selection.
+// All of them are one-pass, 128-bit vectorised, one warp per row with shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace mmcm {
+
+// ------------------------------------------------------------------------------------------------
+// K4 LayerNorm over D (nn.LayerNorm semantics: biased variance, eps inside the sqrt).
+// Replaces layer_norm1/2, pre_layrnorm, post_layernorm, final_layer_norm
+// (HF/models/clip/modeling_clip.py:359-384,522,562,659-661,677,686).
+//   x        fp32 [*, D] residual stream
+//   gather   optional row indices (pooling: only the EOS / CLS rows are normalised) else row i
+//   out_bf16 optional bf16 [rows, D]  (operand of the next GEMM)
+//   out_f32  optional fp32 [rows, D]  (may alias x when gather == nullptr: pre_layrnorm in place)
+// One warp per row; D/128 float4 per lane held in registers (two-pass mean/variance, no re-read).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float eps, const int rows, const int* __restrict__ gather,
+                 __nv_bfloat16* __restrict__ out_bf16, float* out_f32) {
+  constexpr int V = D / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int src = gather ? gather[warp] : warp;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)src * D);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(g4 + c4), bb = __ldg(b4 + c4);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)warp * D)[c4] = y;
+    if (out_bf16) {
+      uint2 p;
+      p.x = pack_bf16x2(y.x, y.y);
+      p.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_bf16 + (size_t)warp * D)[c4] = p;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 text embeddings + pooling-row selection.
+//   x[b*S+s, :] = token_embedding[ids[b,s]] + position_embedding[s]      (HF clip :234-258)
+//   pool_row[b] = b*S + (first s with ids==eos_id, else 0)               (HF clip :575-584)
+//                 b*S + argmax(ids)   when eos_id == 2 (legacy branch)    (HF clip :564-574)
+//                 b*S + S-1           when eos_id < 0 (SigLIP last token)  (HF siglip :520)
+//   key_valid[b,s] = attention_mask[b,s] != 0 (all ones when mask == nullptr)
+// One warp per token row; lane 0 of the first warp of each sample also does the pooling scan.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                  const float* __restrict__ tok, const float* __restrict__ pos, const int B, const int S,
+                  const int vocab, const int eos_id, float* __restrict__ x, int* __restrict__ pool_row,
+                  uint8_t* __restrict__ key_valid) {
+  constexpr int V = D / 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * S) return;
+  const int b = warp / S, s = warp - b * S;
+  long long id = ids[warp];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;  // torch would raise an index error; clamp instead of reading out of bounds
+  const float4* tr = reinterpret_cast<const float4*>(tok + (size_t)id * D);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (size_t)s * D);
+  float4* xo = reinterpret_cast<float4*>(x + (size_t)warp * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 a = __ldg(tr + lane + 32 * i), p = __ldg(pr + lane + 32 * i);
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    xo[lane + 32 * i] = a;
+  }
+  if (lane == 0) key_valid[warp] = mask ? (mask[warp] != 0 ? 1 : 0) : 1;
+  if (s == 0) {
+    // pooling scan: S <= 77, one warp strided over the row
+    int best = 0;
+    if (eos_id < 0) {
+      best = S - 1;
+    } else if (eos_id == 2) {
+      long long bv = -0x7fffffffffffffffLL - 1;
+      int bi = 0;
+      for (int t = lane; t < S; t += 32) {
+        long long v = (long long)(int)ids[(size_t)b * S + t];  // HF casts to int32 before argmax
+        if (v > bv) { bv = v; bi = t; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        long long ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      best = bi;
+    } else {
+      int first = S;
+      for (int t = lane; t < S; t += 32)
+        if ((int)ids[(size_t)b * S + t] == eos_id) { first = t; break; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      best = (first == S) ? 0 : first;
+    }
+    if (lane == 0) pool_row[b] = b * S + best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a im2col + cast for the patch-embedding convolution (stride == kernel == patch):
+//   A[b*P + py*G + px, c*p*p + ky*p + kx] = pixel_values[b, c, py*p + ky, px*p + kx]   (bf16)
+// which makes Conv2d(3, D, p, p) (HF clip :148-154,209-210) the GEMM A @ W.view(D, 3*p*p)^T.
+// Each thread converts 8 consecutive kx (two float4 loads -> one 16-byte store).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ A, const int B, const int img,
+              const int p) {
+  const int G = img / p;
+  const int K = 3 * p * p;
+  const int chunks_per_row = K / 8;
+  const size_t total = (size_t)B * G * G * chunks_per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks_per_row);
+    const size_t row = i / chunks_per_row;
+    const int k = ch * 8;
+    const int c = k / (p * p), rem = k - c * p * p;
+    const int ky = rem / p, kx = rem - ky * p;
+    const int b = (int)(row / (G * G)), pr = (int)(row - (size_t)b * G * G);
+    const int py = pr / G, pxi = pr - py * G;
+    const float* src = px + (((size_t)b * 3 + c) * img + (py * p + ky)) * img + pxi * p + kx;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(d.x, d.y); o.w = pack_bf16x2(d.z, d.w);
+    *reinterpret_cast<uint4*>(A + row * K + k) = o;
+  }
+}
+
+// CLIP class-token rows: x[b*T + 0, :] = class_embedding + position_embedding[0]   (HF clip :212-217)
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                                const int B, const int T, const int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i - b * D;
+  x[(size_t)b * T * D + d] = cls[d] + pos[d];
+}
+
+// pool_row[b] = b*T + t0  (vision CLS row)
+__global__ void fill_pool_rows_kernel(int* __restrict__ pool_row, const int B, const int T, const int t0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) pool_row[b] = b * T + t0;
+}
+
+// fp32 -> bf16 (weights repack; `scale` folds dh^-1/2 into the Q projection -- exact, 1/8 is a power of two)
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, const size_t n,
+                                 const float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i] * scale);
+}
+__global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, const size_t n,
+                                 const float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * scale;
+}
+
+}  // namespace mmcm

@@ -1,0 +1,143 @@
+"""Thin Python owner of one `mmcm_handle` (include/mmcm.h).
+
+Holds no arithmetic: it converts torch tensors to raw pointers, forwards the call on torch's current CUDA
+stream and maps C status codes to the exceptions the reference raises for the same conditions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import arch as A
+from . import lib as L
+
+
+def _cfg_struct(a: A.ArchCfg, head: int, num_outputs: int, fusion_dim: int, head_hidden_dim: int) -> L.MmcmConfig:
+    c = L.MmcmConfig()
+    c.backend, c.head = a.backend, head
+    c.text_hidden, c.text_heads, c.text_layers, c.text_ffn, c.text_act = (
+        a.text.hidden, a.text.heads, a.text.layers, a.text.ffn, a.text.act)
+    c.vis_hidden, c.vis_heads, c.vis_layers, c.vis_ffn, c.vis_act = (
+        a.vision.hidden, a.vision.heads, a.vision.layers, a.vision.ffn, a.vision.act)
+    c.text_eps, c.vis_eps = a.text.eps, a.vision.eps
+    c.vocab, c.max_pos, c.eos_id = a.vocab, a.max_pos, a.eos_id
+    c.image, c.patch, c.proj_dim = a.image, a.patch, a.proj_dim
+    c.fusion_dim, c.num_outputs, c.head_hidden_dim = fusion_dim, num_outputs, head_hidden_dim or 0
+    return c
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One scoring engine bound to one CUDA device."""
+
+    def __init__(self, a: A.ArchCfg, head: int, num_outputs: int, fusion_dim: int = 512,
+                 head_hidden_dim: int = 0, device: int = 0):
+        self.lib = L.load()
+        self.arch, self.head, self.num_outputs = a, head, num_outputs
+        self.device = int(device)
+        self._h = C.c_void_p()
+        cfg = _cfg_struct(a, head, num_outputs, fusion_dim, head_hidden_dim)
+        L.check(self.lib.mmcm_create(C.byref(cfg), self.device, C.byref(self._h)))
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.mmcm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Push every floating-point entry of a reference state dict; the library repacks its own copy."""
+        for key, t in sd.items():
+            if not torch.is_tensor(t) or not t.is_floating_point():
+                continue  # e.g. `embeddings.position_ids` (int64 buffer in transformers<4.31 checkpoints)
+            src = t.detach().to(torch.float32).contiguous()
+            L.check(self.lib.mmcm_load_weight(self._h, key.encode(), src.data_ptr(), src.numel()))
+        L.check(self.lib.mmcm_finalize_weights(self._h))
+
+    def set_option(self, name: str, value: int) -> None:
+        L.check(self.lib.mmcm_set_option(self._h, name.encode(), int(value)))
+
+    # ------------------------------------------------------------------ hot path
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], pixel_values: torch.Tensor,
+                text_present: torch.Tensor, image_present: torch.Tensor, want_probs: bool = False):
+        """Device tensors in, device logits (and optionally sigmoid probabilities) out; enqueued on the current stream."""
+        for nm, t in (("input_ids", input_ids), ("pixel_values", pixel_values), ("text_present", text_present),
+                      ("image_present", image_present), ("attention_mask", attention_mask)):
+            if t is not None and not t.is_cuda:
+                raise RuntimeError(f"{nm} must be a CUDA tensor: the B200 scoring path has no CPU fallback")
+        a = self.arch
+        if pixel_values.dim() != 4 or pixel_values.shape[1] != 3 or pixel_values.shape[2] != a.image \
+                or pixel_values.shape[3] != a.image:
+            # HF/models/clip/modeling_clip.py:204-207
+            raise ValueError(f"Input image size ({pixel_values.shape[-2]}*{pixel_values.shape[-1]}) doesn't match model "
+                             f"({a.image}*{a.image}).")
+        B, S = input_ids.shape
+        dev = input_ids.device
+        ids = input_ids.to(torch.int64).contiguous()
+        mask = None if attention_mask is None else attention_mask.to(torch.int64).contiguous()
+        px = pixel_values.to(torch.float32).contiguous()
+        tp = text_present.to(torch.float32).contiguous()
+        ip = image_present.to(torch.float32).contiguous()
+        if px.shape[0] != B or tp.numel() != B or ip.numel() != B or (mask is not None and mask.shape != ids.shape):
+            raise ValueError("batch dimensions of the inputs disagree")
+        logits = torch.empty((B, self.num_outputs), dtype=torch.float32, device=dev)
+        probs = torch.empty_like(logits) if want_probs else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        L.check(self.lib.mmcm_forward(self._h, ids.data_ptr(), _ptr(mask), px.data_ptr(), tp.data_ptr(), ip.data_ptr(),
+                                      B, S, logits.data_ptr(), _ptr(probs), C.c_void_p(stream)))
+        # the inputs above may be temporaries (dtype casts): keep them alive until the stream has consumed them
+        for t in (ids, mask, px, tp, ip):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream(dev))
+        return (logits, probs) if want_probs else logits
+
+    def forward_host(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], pixel_values: torch.Tensor,
+                     text_present: torch.Tensor, image_present: torch.Tensor, want_probs: bool = False,
+                     out: Optional[torch.Tensor] = None):
+        """HOST tensors in (pinned recommended), HOST logits out: H2D, towers, head and D2H inside one call."""
+        for t in (input_ids, attention_mask, pixel_values, text_present, image_present):
+            if t is not None and t.is_cuda:
+                raise RuntimeError("forward_host takes host tensors")
+        B, S = input_ids.shape
+        ids = input_ids.to(torch.int64).contiguous()
+        mask = None if attention_mask is None else attention_mask.to(torch.int64).contiguous()
+        px = pixel_values.to(torch.float32).contiguous()
+        tp = text_present.to(torch.float32).contiguous()
+        ip = image_present.to(torch.float32).contiguous()
+        logits = out if out is not None else torch.empty((B, self.num_outputs), dtype=torch.float32).pin_memory()
+        probs = torch.empty((B, self.num_outputs), dtype=torch.float32).pin_memory() if want_probs else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.mmcm_forward_host(self._h, ids.data_ptr(), _ptr(mask), px.data_ptr(), tp.data_ptr(),
+                                           ip.data_ptr(), B, S, logits.data_ptr(), _ptr(probs), C.c_void_p(stream)))
+        return (logits, probs) if want_probs else logits
+
+    # ------------------------------------------------------------------ introspection
+    def stage(self, name: str) -> torch.Tensor:
+        n = C.c_int64(0)
+        L.check(self.lib.mmcm_get_stage(self._h, name.encode(), None, 0, C.byref(n), None))
+        out = torch.empty(max(n.value, 1), dtype=torch.float32, device=f"cuda:{self.device}")
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        L.check(self.lib.mmcm_get_stage(self._h, name.encode(), out.data_ptr(), out.numel(), C.byref(n),
+                                        C.c_void_p(stream)))
+        return out[: n.value]
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.mmcm_last_launch_count(self._h))
+
+    def gemm_time(self):
+        ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        L.check(self.lib.mmcm_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- samples/s of the scoring hot path (CLIP-Fusion B/32 forward: ids, mask, pixels, flags -> logits).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model clip_fusion|clip_mtl|siglip_fusion] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...         # the CPU arm (oracle port of the reference's fp32 forward)
+
+One "step" = one pass of the hot path over one synthetic batch of B samples per GPU (weak scaling: every rank
+scores its own shard, weights replicated, the only collective is the gather of the [B, C] scores each step).
+`value` is timed with CUDA events with the inputs resident in HBM; `e2e` is the same metric through the
+host-buffer C-ABI call (mmcm_forward_host: pinned host inputs, H2D + D2H inside the timed region).
+Prints exactly ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    # name: (kind, arch attr, encoder name, ctor kwargs)
+    "clip_fusion": ("fusion", "CLIP_B32", "openai/clip-vit-base-patch32", dict(backend="clip")),
+    "clip_mtl": ("mtl", "CLIP_B32", "openai/clip-vit-base-patch32", dict(head_hidden_dim=256)),
+    "siglip_fusion": ("fusion", "SIGLIP2_B16", "google/siglip2-base-patch16-224", dict(backend="siglip")),
+}
+TASKS = ["racist", "sexist", "homophobe", "religion", "otherhate"]
+METRIC = "samples/sec CLIP-Fusion B/32 inference at 1/2/4/8 B200; % tensor-pipe peak"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", 1368.0)), "tflops_burst": float(p.get("bf16_tflops", 1655.0)),
+                "hbm_gbs": float(p.get("hbm_gbs", 6550.0)), "source": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def build_case(model: str):
+    from __graft_entry__ import load_package
+    load_package()
+    from mmcm_b200 import arch as A, synthetic as syn
+    kind, arch_attr, enc, kw = MODELS[model]
+    a = getattr(A, arch_attr)
+    hh = kw.get("head_hidden_dim") or 0
+    spec = A.fusion_spec(a, 5, 512) if kind == "fusion" else A.mtl_spec(a, 5, 512, hh)
+    sd = syn.make_state_dict(spec, a, seed=0, hardened=False)   # default random init: what the official gate is for
+    flops = A.algorithmic_flops_per_sample(a, A.HEAD_FUSION if kind == "fusion" else A.HEAD_MTL, 5, 512, hh)
+    return kind, a, enc, kw, sd, flops
+
+
+def oracle_logits(kind, a, sd, batch):
+    import torch
+    from oracle import scoring_oracle as orc
+    from mmcm_b200 import arch as A
+    with torch.no_grad():
+        if kind == "fusion":
+            return orc.fusion_forward(sd, batch, "clip" if a.backend == A.BACKEND_CLIP else "siglip", a.patch, a.eos_id)
+        return orc.mtl_forward(sd, batch, a.patch, a.eos_id)
+
+
+def cpu_arm(kind, a, sd, batch_size, steps, warmup, seed=1234):
+    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample of the workload."""
+    import torch
+    from mmcm_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = syn.make_inputs(a, batch_size, seed=seed)
+    for _ in range(warmup):
+        oracle_logits(kind, a, sd, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = oracle_logits(kind, a, sd, batch)
+    dt = time.perf_counter() - t0
+    return {"value": batch_size * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": torch.get_num_threads(),
+            "logits": out, "batch": batch}
+
+
+def parity_gate(logits, ref):
+    """Official gate (BASELINE.json north_star) on default random init."""
+    import torch
+    err = (logits - ref).abs().max().item()
+    p, pr = torch.sigmoid(logits), torch.sigmoid(ref)
+    perr = (p - pr).abs().max().item()
+    far = (pr - 0.5).abs() > 1e-3
+    same = bool(((p >= 0.5) == (pr >= 0.5))[far].all())
+    return {"logit_max_abs": err, "prob_max_abs": perr, "decisions_identical": same,
+            "pass": bool(err <= 2e-2 and perr <= 5e-3 and same)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="clip_fusion", choices=sorted(MODELS))
+    ap.add_argument("--batch", type=int, default=1024, help="samples per step per GPU")
+    ap.add_argument("--micro-batch", type=int, default=0, help="engine micro-batch (0 = library default)")
+    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    kind, a, enc, kw, sd, flops = build_case(args.model)
+    workload = (f"{args.model} ({enc} arch, random-init) forward, batch {args.batch}/GPU/step, "
+                f"{a.image}px, {a.max_pos} tok, len~U{{3..{a.max_pos}}}")
+
+    # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        B = 32
+        steps = max(1, min(args.steps, 5))
+        r = cpu_arm(kind, a, sd, B, steps, 1)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "sample": f"batch {B} per step"},
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                 "sample": f"{steps} forwards of batch {B} (oracle/scoring_oracle.py, torch fp32, "
+                                           f"{r['cores']} threads)"},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    import mmcm_b200 as P
+    from mmcm_b200 import synthetic as syn, sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the scoring path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    if kind == "fusion":
+        m = P.MultiModalFusionClassifier(enc, num_labels=5, **kw)
+    else:
+        m = P.MultiTaskClassifier(enc, TASKS, **kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    if args.micro_batch:
+        m.set_option("micro_batch", args.micro_batch)
+    m.set_option("streams", args.streams)
+    eng = m._ensure_engine(local_rank)
+
+    B = args.batch
+    host = syn.make_inputs(a, B, seed=1234 + rank)
+    batch = {k: v.to(dev) for k, v in host.items()}
+    in_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step():
+        logits = m(**batch)["logits"]
+        if world > 1:
+            logits = sharding.gather_scores(logits, B * world)
+        return logits
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    sync_all()
+    launches_per_step = eng.last_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: host buffers through mmcm_forward_host
+    e2e = None
+    if not args.no_e2e:
+        pinned = {k: v.pin_memory() for k, v in host.items()}
+        out_h = torch.empty((B, 5), dtype=torch.float32).pin_memory()
+
+        def estep():
+            return eng.forward_host(pinned["input_ids"], pinned["attention_mask"], pinned["pixel_values"],
+                                    pinned["text_present"], pinned["image_present"], out=out_h)
+        for _ in range(3):
+            estep()
+        sync_all()
+        ksteps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(ksteps):
+            estep()
+        e1.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * ksteps / (ems.item() * 1e-3), "unit": "samples/s",
+               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 5 * 4, "steps": ksteps,
+               "api": "mmcm_forward_host (pinned host buffers, chunked H2D overlapped with the towers)"}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel family
+    peaks = _peaks()
+    roof = None
+    if rank == 0:
+        m.set_option("streams", 1)          # serialise so that the per-GEMM events time only the GEMM
+        m.set_option("time_gemms", 1)
+        m(**batch)
+        torch.cuda.synchronize()
+        gms, gfl, gn = eng.gemm_time()
+        m.set_option("time_gemms", 0)
+        m.set_option("streams", args.streams)
+        achieved = gfl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all encoder GEMMs of one step, CUDA events per launch)",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["source"], "gemm_launches": gn, "gemm_ms_per_step": gms,
+                "gemm_flops_per_step": gfl,
+                "model_algorithmic_tflops": value / world * flops["total"] / 1e12,
+                "model_frac_of_peak": value / world * flops["total"] / 1e12 / peaks["tflops"]}
+
+    # ------------------------------------------------------------------ CPU baseline + parity gate (rank 0, N=1)
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(kind, a, sd, 32, 3, 1)
+        cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+               "sample": "3 forwards of batch 32 (oracle/scoring_oracle.py = fp32 restatement of the reference, torch CPU)"}
+        got = m(**{k: v.to(dev) for k, v in r["batch"].items()})["logits"].float().cpu()
+        parity = parity_gate(got, r["logits"])
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB/step/GPU vs 126 MB)",
+                           "micro_batch": args.micro_batch or "library default", "streams": args.streams,
+                           "algorithmic_gflop_per_sample": flops["total"] / 1e9},
+                "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,
+                "cpu_baseline": cpu, "parity": parity}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -125,9 +125,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on the phase with a generous bound: a protocol bug must trap (launch failure), never hang the GPU.
+// Spin on the phase with a wall-clock bound (4 s): a protocol bug must trap (launch failure), never hang the GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t it = 0; !done; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -136,7 +142,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (it > (1u << 24)) __trap();
+    if (!done && (it & 0x3FFu) == 0x3FFu) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

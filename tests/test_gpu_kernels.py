@@ -1,0 +1,173 @@
+"""Kernel-level parity through the C ABI (mmcm_gemm_bf16 / mmcm_layernorm / mmcm_attention) against a plain
+PyTorch fp32 statement of the same op on the same bf16-rounded operands.  Tolerances are written per test."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mmcm_b200 import lib as L
+    return L.load()
+
+
+def _check(code):
+    from mmcm_b200 import lib as L
+    L.check(code)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+GEMM_SHAPES = [
+    # (M, N, K)   every (N, K) pair the CLIP / SigLIP towers use, with ragged and tiny M
+    (6400, 2304, 768), (6400, 768, 768), (6400, 3072, 768), (6400, 768, 3072),
+    (9856, 1536, 512), (9856, 512, 512), (9856, 2048, 512), (9856, 512, 2048),
+    (392, 768, 3072), (1568, 768, 768), (1568, 1536, 768),
+    (8, 768, 768), (1, 512, 512), (129, 256, 64), (300, 128, 128), (20000, 512, 512),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_gemm_bias_bf16(lib, M, N, K, impl):
+    if impl == 1 and M * N * K > 3e10:
+        pytest.skip("SIMT validation kernel only on small shapes")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 0, 0, out.data_ptr(), None, None,
+                              0, 0, impl, _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    # fp32 accumulation of exact bf16 products; the only rounding is the final bf16 store (rel 2^-9)
+    err = (out.float() - ref).abs()
+    assert (err <= 1e-2 * ref.abs() + 2e-2).all(), f"max err {err.max().item()}"
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_bias_act(lib, act):
+    M, N, K = 1000, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(act)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5 * 2).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 1, act, out.data_ptr(), None, None,
+                              0, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    pre = A.float() @ W.float().t() + bias
+    ref = _quick_gelu(pre) if act == 1 else torch.nn.functional.gelu(pre, approximate="tanh")
+    err = (out.float() - ref).abs()
+    assert (err <= 1e-2 * ref.abs() + 1e-2).all(), f"max err {err.max().item()}"
+
+
+def test_gemm_bias_residual_in_place(lib):
+    M, N, K = 777, 768, 3072
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + A.float() @ W.float().t() + bias
+    _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 2, 0, x.data_ptr(), x.data_ptr(),
+                              None, 0, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 2e-3   # fp32 out: summation order only
+
+
+def test_gemm_patch_epilogue(lib):
+    """rows of the im2col GEMM land at token 1..49 of each sample with the position embedding added."""
+    Bn, P, T, N, K = 5, 49, 50, 768, 3072
+    M = Bn * P
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.02).bfloat16()
+    pos = torch.randn(T, N, device="cuda", generator=g)
+    out = torch.full((Bn * T, N), 123.0, device="cuda")
+    _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), None, M, N, K, 3, 0, out.data_ptr(), None, pos.data_ptr(),
+                              P, T, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t()).view(Bn, P, N) + pos[1:][None]
+    o = out.view(Bn, T, N)
+    assert (o[:, 1:] - ref).abs().max().item() < 2e-3
+    assert (o[:, 0] == 123.0).all()                # class rows are not touched by the GEMM
+
+
+def test_gemm_rejects_bad_shapes(lib):
+    A = torch.zeros(4, 96, device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(4, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), None, 4, 128, 96, 0, 0, out.data_ptr(), None, None, 0, 0,
+                                  0, _stream()))
+
+
+@pytest.mark.parametrize("D", [512, 768])
+@pytest.mark.parametrize("rows", [1, 50, 12800])
+def test_layernorm(lib, D, rows):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 1
+    gam = torch.randn(D, device="cuda", generator=g)
+    bet = torch.randn(D, device="cuda", generator=g)
+    ob = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    of = torch.empty(rows, D, device="cuda")
+    _check(lib.mmcm_layernorm(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-5, rows, D, ob.data_ptr(), of.data_ptr(),
+                              _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-5)
+    assert (of - ref).abs().max().item() < 1e-4               # fp32 in, fp32 statistics, fp32 out
+    assert (ob.float() - ref).abs().max().item() <= 8e-3 * ref.abs().max().item() + 1e-3   # bf16 store
+
+
+def _ref_attention(qkv, B, T, H, causal, kvalid):
+    D = H * 64
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)   # [B,H,T,64] each; q is pre-scaled
+    s = q @ k.transpose(-1, -2)
+    allow = torch.ones(B, 1, T, T, dtype=torch.bool, device=qkv.device)
+    if causal:
+        allow = allow & torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
+    if kvalid is not None:
+        allow = allow & (kvalid.view(B, 1, 1, T) != 0)
+    s = s.masked_fill(~allow, float("-inf"))
+    dead = ~allow.any(-1, keepdim=True)
+    p = torch.softmax(s.masked_fill(dead, 0.0), -1).masked_fill(dead, 0.0)
+    return (p @ v).transpose(1, 2).reshape(B * T, D)
+
+
+@pytest.mark.parametrize("T,H,causal,masked", [
+    (50, 12, 0, False), (77, 8, 1, False), (77, 8, 1, True), (64, 12, 0, True), (196, 12, 0, False),
+    (11, 8, 1, True), (33, 8, 0, True), (128, 4, 1, True), (250, 2, 0, True)])
+def test_attention(lib, T, H, causal, masked):
+    B = 6
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(T * 13 + H)
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g)
+    qkv[:, :D] *= 0.125 * 2.0     # scale folded into q; x2 for peaky softmaxes
+    qkv = qkv.bfloat16()
+    kvalid = None
+    if masked:
+        lens = torch.randint(1, T + 1, (B,), device="cuda", generator=g)
+        kvalid = (torch.arange(T, device="cuda")[None] < lens[:, None]).to(torch.uint8)
+        kvalid[0] = 0             # fully masked sample: every query row must come out exactly 0
+        kvalid = kvalid.contiguous()
+    out = torch.full((B * T, D), 7.0, device="cuda", dtype=torch.bfloat16)
+    _check(lib.mmcm_attention(qkv.data_ptr(), None if kvalid is None else kvalid.data_ptr(), B, T, H, causal,
+                              out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, B, T, H, causal, kvalid)
+    # P is rounded to bf16 before P V and the output is stored as bf16: 2^-8 relative on O(1) values
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    if masked:
+        assert (out.view(B, T, D)[0] == 0).all()

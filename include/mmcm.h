@@ -113,7 +113,10 @@ MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
  * mmcm_set_option(h, "time_gemms", 1); also returns their FLOPs. Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 /* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05, 1 = SIMT validation kernel),
- * "micro_batch" (samples per internal pass), "streams" (1 or 2: text/vision towers on separate streams). */
+ * "micro_batch" (upper bound on the samples per internal pass of a tower), "auto_chunk" (1 = pick, per tower, the
+ * chunk size <= micro_batch whose GEMM tile counts fill whole waves of the 148 SMs; 0 = use micro_batch as is),
+ * "streams" (1 or 2: text/vision towers on separate streams), "debug_feats" (0/1: keep the projected
+ * features of the fusion head for mmcm_get_stage "text_feat"/"vision_feat"). */
 MMCM_API int mmcm_set_option(mmcm_handle h, const char* name, int64_t value);
 MMCM_API const char* mmcm_last_error(void);
 MMCM_API const char* mmcm_version(void);

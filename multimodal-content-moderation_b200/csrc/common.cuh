@@ -45,6 +45,25 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
+// MUFU-light variants for the GEMM epilogue (one tanh.approx per element instead of ex2 + rcp; max relative error of
+// tanh.approx.f32 is 2^-11, below the 2^-9 rounding of the bf16 store that follows):
+//   x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x))
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(0.851f * x), h);
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u = x * fmaf(k0k1, x * x, k0);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(u), h);
+}
+
 // exact GELU (erf), nn.GELU() default -- used by the fp32 heads (fusion.py:143, multitask.py:101)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

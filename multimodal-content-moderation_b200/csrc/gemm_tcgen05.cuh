@@ -12,8 +12,12 @@
 //                                 accumulators live in TMEM; tcgen05.commit frees ring slots / publishes tiles
 //   * warp 2   : TMEM allocator (2 x BLOCK_N columns: the accumulator is double buffered so the epilogue
 //                                 of tile i overlaps the main loop of tile i+1)
-//   * warps 4-7: epilogue      -- tcgen05.ld 32x32b.x32 (lane == output row), fused bias/act/residual,
-//                                 128-bit global stores
+//   * warps 4-11: epilogue     -- tcgen05.ld 32x32b.x32 (lane == output row), fused bias/act in registers, then a
+//                                 per-warp shared-memory transpose so that every global access (bf16 / fp32 store,
+//                                 fp32 residual or position-embedding read) is a full 128-byte line per row:
+//                                 warps e and e+4 share TMEM lanes 32*(e%4).. and split the tile's columns
+//   * tiles are handed out by a global atomic counter (dynamic persistent scheduler): when the text and the vision
+//     tower run on two streams, late-starting CTAs simply take fewer tiles
 //   Both operands are K-major, which is exactly nn.Linear's [out,in] weight layout: no transposes anywhere.
 #pragma once
 #include <cuda.h>
@@ -54,62 +58,134 @@ __device__ __forceinline__ void epi_store1(const EpiParams& ep, int row, int col
   }
 }
 
-// one output row, 32 consecutive columns starting at col0 (col0 % 32 == 0)
+// ---- coalesced epilogue -------------------------------------------------------------------------
+// A warp owns 32 accumulator rows (lane == row).  A chunk is 128 bytes of output per row (32 fp32 or 64 bf16
+// columns).  Half a warp at a time writes its rows into a padded 16-row staging tile (pitch 144 B: conflict-free
+// for 16-byte accesses), then the whole warp re-reads it so that 8 lanes cover one row: every global instruction
+// touches 4 complete 128-byte lines instead of 32 partial ones.
+constexpr int EPI_PITCH = 144;                   // bytes per staged row
+constexpr int EPI_STAGE_BYTES = 16 * EPI_PITCH;  // per epilogue warp
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// bf16 outputs: 64 columns starting at col0 (two TMEM loads), rows row_base .. row_base+31
 template <int EPI>
-__device__ __forceinline__ void epi_store32(const EpiParams& ep, int row, int col0, const uint32_t (&r)[32]) {
-  float v[32];
+__device__ __forceinline__ void epi_chunk_bf16(const EpiParams& ep, const uint32_t stage, const int lane,
+                                               const int row_base, const int col0, const int M,
+                                               const uint32_t (&r0)[32], const uint32_t (&r1)[32]) {
+  uint32_t w[32];
+  const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (ep.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+  for (int i = 0; i < 8; ++i) {
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(i < 4 ? r0[8 * i + j] : r1[8 * (i - 4) + j]);
+    if (ep.bias) {
+      const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+      v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
+      v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
     }
-  }
-  if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) {
     if (EPI == EPI_BIAS_ACT_BF16) {
       if (ep.act == ACT_QUICK_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        for (int j = 0; j < 8; ++j) v[j] = quick_gelu_fast(v[j]);
       } else if (ep.act == ACT_GELU_TANH) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+        for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0);
+    w[4 * i + 0] = pack_bf16x2(v[0], v[1]);
+    w[4 * i + 1] = pack_bf16x2(v[2], v[3]);
+    w[4 * i + 2] = pack_bf16x2(v[4], v[5]);
+    w[4 * i + 3] = pack_bf16x2(v[6], v[7]);
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+  const int sub = lane >> 3, c16 = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 w;
-      w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      o[i] = w;
-    }
-  } else if (EPI == EPI_BIAS_RESID_F32) {
-    size_t off = (size_t)row * ep.ldo + col0;
-    const float4* rs = reinterpret_cast<const float4*>(ep.resid + off);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
-    const bool has_resid = ep.resid != nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((lane >> 4) == pass) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = has_resid ? rs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      x.x += v[4 * i + 0]; x.y += v[4 * i + 1]; x.z += v[4 * i + 2]; x.w += v[4 * i + 3];
-      o[i] = x;
+      for (int i = 0; i < 8; ++i)
+        sts128(stage + (lane & 15) * EPI_PITCH + i * 16, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     }
-  } else {
-    int b = row / ep.P, p = row - b * ep.P, poff = ep.T - ep.P;
-    const float4* ps = reinterpret_cast<const float4*>(ep.pos + (size_t)(poff + p) * ep.ldo + col0);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) +
-                                          ((size_t)b * ep.T + poff + p) * ep.ldo + col0);
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = __ldg(ps + i);
-      x.x += v[4 * i + 0]; x.y += v[4 * i + 1]; x.z += v[4 * i + 2]; x.w += v[4 * i + 3];
-      o[i] = x;
+    for (int it = 0; it < 4; ++it) {
+      const int rl = it * 4 + sub;
+      const uint4 v = lds128(stage + rl * EPI_PITCH + c16 * 16);
+      const int row = row_base + pass * 16 + rl;
+      if (row < M) *reinterpret_cast<uint4*>(out + (size_t)row * ep.ldo + col0 + c16 * 8) = v;
     }
+    __syncwarp();
+  }
+}
+
+// fp32 outputs: 32 columns starting at col0.  The addend (residual stream or position embedding) of a chunk is 8
+// float4 per lane; it is loaded by `epi_load_addend` BEFORE the accumulator is waited for (the residual may alias
+// the output, so the compiler cannot hoist these loads above earlier stores by itself -- a load->store->load chain
+// of L2 round trips is what made the first version of this epilogue 5x slower than its MMAs).
+template <int EPI>
+__device__ __forceinline__ void epi_load_addend(const EpiParams& ep, const int lane, const int row_base,
+                                                const int col0, const int M, float4 (&x)[8]) {
+  const int sub = lane >> 3, c16 = lane & 7;
+  const int col = col0 + c16 * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + i * 4 + sub;   // i = pass * 4 + it
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < M) {
+      if (EPI == EPI_BIAS_RESID_F32) {
+        if (ep.resid) x[i] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldo + col);
+      } else {
+        const int b = row / ep.P, p = row - b * ep.P;
+        x[i] = __ldg(reinterpret_cast<const float4*>(ep.pos + (size_t)(ep.T - ep.P + p) * ep.ldo + col));
+      }
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_chunk_f32(const EpiParams& ep, const uint32_t stage, const int lane,
+                                              const int row_base, const int col0, const int M,
+                                              const uint32_t (&r)[32], const float4 (&x)[8]) {
+  float* out = reinterpret_cast<float*>(ep.out);
+  const int sub = lane >> 3, c16 = lane & 7;
+  const int col = col0 + c16 * 4;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((lane >> 4) == pass) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        sts128(stage + (lane & 15) * EPI_PITCH + i * 16, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rl = it * 4 + sub;
+      const uint4 u = lds128(stage + rl * EPI_PITCH + c16 * 16);
+      const float4 a = x[pass * 4 + it];
+      const float4 v = make_float4(__uint_as_float(u.x) + bias.x + a.x, __uint_as_float(u.y) + bias.y + a.y,
+                                   __uint_as_float(u.z) + bias.z + a.z, __uint_as_float(u.w) + bias.w + a.w);
+      const int row = row_base + pass * 16 + rl;
+      if (row < M) {
+        if (EPI == EPI_BIAS_RESID_F32) {
+          *reinterpret_cast<float4*>(out + (size_t)row * ep.ldo + col) = v;
+        } else {  // EPI_PATCH_F32: GEMM row (sample b, patch p) -> token row b*T + (T-P) + p
+          const int b = row / ep.P, p = row - b * ep.P;
+          *reinterpret_cast<float4*>(out + ((size_t)b * ep.T + ep.T - ep.P + p) * ep.ldo + col) = v;
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -230,26 +306,33 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024: 1 KB alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                   // double-buffered accumulator
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+  static constexpr int SCHED_SLOTS = 4;
 };
 
+// sched[0] = next tile, sched[1] = CTAs finished (the last one re-arms both for the next launch on this stream)
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const EpiParams ep, const int M, const int N, const int K) {
+                    const EpiParams ep, const int M, const int N, const int K, int* __restrict__ sched) {
   using C = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES];
   __shared__ __align__(8) uint64_t bar_empty[C::STAGES];
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_sfull[C::SCHED_SLOTS];
+  __shared__ __align__(8) uint64_t bar_sempty[C::SCHED_SLOTS];
+  __shared__ int sched_tile[C::SCHED_SLOTS];
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B aligned tiles
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
 
   const int tiles_n = N / BLOCK_N;
   const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
@@ -267,7 +350,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 128);  // every epilogue thread arrives
+      mbar_init(smem_u32(&bar_tempty[s]), C::EPI_WARPS);  // lane 0 of every epilogue warp arrives
+    }
+    for (int s = 0; s < C::SCHED_SLOTS; ++s) {
+      mbar_init(smem_u32(&bar_sfull[s]), 1);
+      mbar_init(smem_u32(&bar_sempty[s]), 1 + C::EPI_WARPS);  // MMA warp + every epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -279,10 +366,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // ===================== tile scheduler + TMA producer =====================
+    int stage = 0, slot = 0;
+    uint32_t phase = 0, sphase = 0;
+    while (true) {
+      mbar_wait(smem_u32(&bar_sempty[slot]), sphase ^ 1u);
+      int tile = 0;
+      if (lane == 0) {
+        tile = atomicAdd(&sched[0], 1);
+        if (tile >= num_tiles) tile = -1;
+        sched_tile[slot] = tile;
+        mbar_arrive(smem_u32(&bar_sfull[slot]));
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (++slot == C::SCHED_SLOTS) { slot = 0; sphase ^= 1u; }
+      if (tile < 0) break;
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -297,12 +395,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
+    if (lane == 0) {
+      __threadfence();
+      const int done = atomicAdd(&sched[1], 1);
+      if (done == (int)gridDim.x - 1) {  // every CTA has drawn its last tile: re-arm for the next launch
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16(C::BLOCK_M, BLOCK_N);
-    int stage = 0, as = 0;
-    uint32_t phase = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int stage = 0, as = 0, slot = 0;
+    uint32_t phase = 0, aphase = 0, sphase = 0;
+    while (true) {
+      mbar_wait(smem_u32(&bar_sfull[slot]), sphase);
+      const int tile = sched_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_sempty[slot]));
+      if (++slot == C::SCHED_SLOTS) { slot = 0; sphase ^= 1u; }
+      if (tile < 0) break;
       mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
@@ -328,25 +441,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (as == 0) aphase ^= 1u;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps; warp w owns TMEM lanes 32*(w%4)..+31) =====================
-    const int ew = warp & 3;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // ===================== epilogue: warp e owns TMEM lanes 32*(e%4).., columns half (e/4) =====================
+    const int e = warp - 4;
+    const int lg = e & 3, ch = e >> 2;
+    const uint32_t stage_smem = epi_base + e * EPI_STAGE_BYTES;
+    constexpr int HALF_N = BLOCK_N / 2;
+    int as = 0, slot = 0;
+    uint32_t aphase = 0, sphase = 0;
+    while (true) {
+      mbar_wait(smem_u32(&bar_sfull[slot]), sphase);
+      const int tile = sched_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_sempty[slot]));
+      if (++slot == C::SCHED_SLOTS) { slot = 0; sphase ^= 1u; }
+      if (tile < 0) break;
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int row_base = m_blk * C::BLOCK_M + lg * 32;
+      const int col_base = n_blk * BLOCK_N + ch * HALF_N;
+      constexpr bool kF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32);
+      float4 xa[8];
+      if (kF32 && row_base < M) epi_load_addend<EPI>(ep, lane, row_base, col_base, M, xa);  // overlaps the MMAs
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
-      const int row = m_blk * C::BLOCK_M + ew * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BLOCK_N + ch * HALF_N);
+      if (row_base < M) {
+        if (!kF32) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (row < M) epi_store32<EPI>(ep, row, n_blk * BLOCK_N + c * 32, r);
+          for (int c = 0; c < HALF_N / 64; ++c) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + (uint32_t)(c * 64), r0);
+            tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r1);
+            tmem_ld_wait();
+            epi_chunk_bf16<EPI>(ep, stage_smem, lane, row_base, col_base + c * 64, M, r0, r1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < HALF_N / 32; ++c) {
+            uint32_t r[32];
+            float4 xn[8];
+            tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            if (c + 1 < HALF_N / 32) epi_load_addend<EPI>(ep, lane, row_base, col_base + (c + 1) * 32, M, xn);
+            tmem_ld_wait();
+            epi_chunk_f32<EPI>(ep, stage_smem, lane, row_base, col_base + c * 32, M, r, xa);
+            if (c + 1 < HALF_N / 32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xa[i] = xn[i];
+            }
+          }
+        }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&bar_tempty[as]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -132,6 +133,26 @@ static int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, 
   return MMCM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ tile scheduler state
+// One {next tile, finished CTAs} pair per stream: launches on a stream are serialised and every launch leaves the
+// pair at {0, 0} (the last CTA re-arms it), so no memset is needed between GEMMs.
+static std::map<std::pair<int, cudaStream_t>, int*> g_sched;
+static int get_sched(cudaStream_t st, int** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto key = std::make_pair(dev, st);
+  auto it = g_sched.find(key);
+  if (it == g_sched.end()) {
+    int* p = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&p), 2 * sizeof(int)));
+    CK(cudaMemset(p, 0, 2 * sizeof(int)));
+    it = g_sched.emplace(key, p).first;
+  }
+  *out = it->second;
+  return MMCM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ launch counting
 struct LaunchStats {
   int64_t launches = 0;
@@ -150,7 +171,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+  int* sched = nullptr;
+  CKR(get_sched(st, &sched));
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K, sched);
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -339,7 +362,8 @@ struct mmcm_handle_s {
   cudaEvent_t ev_fork = nullptr, ev_text = nullptr, ev_vis = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
   // options
-  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 128, opt_debug_feats = 0;
+  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 256, opt_debug_feats = 0, opt_auto_chunk = 1;
+  int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
 };
 typedef mmcm_handle_s Eng;
@@ -591,32 +615,69 @@ static int vis_tokens(const mmcm_config& c) {
   return G * G + (c.backend == MMCM_BACKEND_CLIP ? 1 : 0);
 }
 
-static int ensure_arenas(Eng* e, int mb) {
+static int ensure_arenas(Eng* e, int mbt, int mbv) {
   const mmcm_config& c = e->cfg;
-  if (mb <= e->mb_text && mb <= e->mb_vis) return MMCM_OK;
-  CK(cudaDeviceSynchronize());
-  free_arena(e, e->at);
-  free_arena(e, e->av);
-  dfree(e, e->im2col); dfree(e, e->key_valid);
-  dfree(e, e->map_kv); dfree(e, e->map_att); dfree(e, e->map_h); dfree(e, e->map_ff); dfree(e, e->map_y);
-  e->im2col = nullptr; e->key_valid = nullptr;
-  e->map_kv = e->map_att = e->map_h = e->map_ff = nullptr; e->map_y = nullptr;
-  const int Tv = vis_tokens(c);
-  const int G = c.image / c.patch, P = G * G, Kp = 3 * c.patch * c.patch;
-  CKR(alloc_arena(e, e->at, e->text, (int64_t)mb * c.max_pos, mb));
-  CKR(alloc_arena(e, e->av, e->vis, (int64_t)mb * Tv, mb));
-  CKR(dalloc(e, &e->im2col, (int64_t)mb * P * Kp));
-  CKR(dalloc(e, &e->key_valid, (int64_t)mb * c.max_pos));
-  if (c.backend == MMCM_BACKEND_SIGLIP) {
-    const int D = c.vis_hidden;
-    CKR(dalloc(e, &e->map_kv, (int64_t)mb * Tv * 2 * D));
-    CKR(dalloc(e, &e->map_att, (int64_t)mb * D));
-    CKR(dalloc(e, &e->map_h, (int64_t)mb * D));
-    CKR(dalloc(e, &e->map_ff, (int64_t)mb * c.vis_ffn));
-    CKR(dalloc(e, &e->map_y, (int64_t)mb * D));
+  if (mbt > e->mb_text) {
+    CK(cudaDeviceSynchronize());
+    free_arena(e, e->at);
+    dfree(e, e->key_valid);
+    e->key_valid = nullptr;
+    CKR(alloc_arena(e, e->at, e->text, (int64_t)mbt * c.max_pos, mbt));
+    CKR(dalloc(e, &e->key_valid, (int64_t)mbt * c.max_pos));
+    e->mb_text = mbt;
   }
-  e->mb_text = e->mb_vis = mb;
+  if (mbv > e->mb_vis) {
+    CK(cudaDeviceSynchronize());
+    free_arena(e, e->av);
+    dfree(e, e->im2col);
+    dfree(e, e->map_kv); dfree(e, e->map_att); dfree(e, e->map_h); dfree(e, e->map_ff); dfree(e, e->map_y);
+    e->im2col = nullptr;
+    e->map_kv = e->map_att = e->map_h = e->map_ff = nullptr; e->map_y = nullptr;
+    const int Tv = vis_tokens(c);
+    const int G = c.image / c.patch, P = G * G, Kp = 3 * c.patch * c.patch;
+    CKR(alloc_arena(e, e->av, e->vis, (int64_t)mbv * Tv, mbv));
+    CKR(dalloc(e, &e->im2col, (int64_t)mbv * P * Kp));
+    if (c.backend == MMCM_BACKEND_SIGLIP) {
+      const int D = c.vis_hidden;
+      CKR(dalloc(e, &e->map_kv, (int64_t)mbv * Tv * 2 * D));
+      CKR(dalloc(e, &e->map_att, (int64_t)mbv * D));
+      CKR(dalloc(e, &e->map_h, (int64_t)mbv * D));
+      CKR(dalloc(e, &e->map_ff, (int64_t)mbv * c.vis_ffn));
+      CKR(dalloc(e, &e->map_y, (int64_t)mbv * D));
+    }
+    e->mb_vis = mbv;
+  }
   return MMCM_OK;
+}
+
+// ---- micro-batch selection ------------------------------------------------------------------------
+// The persistent GEMMs hand out 128 x 256 tiles to 148 CTAs, so a launch costs ceil(tiles / 148) "rounds": a chunk
+// of 128 samples of the CLIP text tower is 77 row blocks x 2 column blocks = 154 tiles = TWO rounds for out_proj/fc2,
+// a chunk of 123 samples is 148 tiles = one.  Pick, per tower, the chunk size (<= cap) that minimises the modelled
+// cycles of the whole batch: rounds * (k-blocks * 512 + epilogue) per GEMM + a fixed cost per launch.
+static double chunk_cost(const TowerW& t, int T, int n, int sms) {
+  if (n <= 0) return 0.0;
+  const double mt = std::ceil((double)n * T / 128.0);
+  auto gemm = [&](int N, int K) {
+    const int bn = (N % 256 == 0) ? 256 : 128;
+    const double rounds = std::ceil(mt * (N / bn) / (double)sms);
+    return rounds * ((K / 64) * 512.0 * bn / 256.0 + 2500.0) + 6000.0;
+  };
+  const double layer = gemm(3 * t.D, t.D) + gemm(t.D, t.D) + gemm(t.F, t.D) + gemm(t.D, t.F) +
+                       3 * 6000.0 /* LN, LN, attention launches */ + 3.0 * n * T * t.D / 148.0 / 64.0;
+  return layer * t.L;
+}
+static int choose_chunk(const TowerW& t, int T, int B, int cap, int sms) {
+  if (cap > B) cap = B;
+  int best = cap;
+  double best_cost = 1e300;
+  for (int c = cap; c >= 16 || c == cap; --c) {
+    if (c < 1) break;
+    const int full = B / c, rem = B - full * c;
+    const double cost = full * chunk_cost(t, T, c, sms) + chunk_cost(t, T, rem, sms);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 static int ensure_batch(Eng* e, int64_t B) {
@@ -786,9 +847,11 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
   e->stats.launches = 0;
   clear_gemm_events(e->stats);
   if (B == 0) return MMCM_OK;
-  int mb = e->opt_micro_batch;
-  if (mb > B) mb = B;
-  CKR(ensure_arenas(e, mb));
+  const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min(B, e->opt_micro_batch);
+  const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, e->opt_micro_batch, g_num_sms)
+                                   : std::min(B, e->opt_micro_batch);
+  e->last_chunk_text = ct; e->last_chunk_vis = cv;
+  CKR(ensure_arenas(e, ct, cv));
   CKR(ensure_batch(e, B));
   const bool two = e->opt_streams >= 2;
   cudaStream_t stx = two ? e->s_text : st, svx = two ? e->s_vis : st;
@@ -798,11 +861,19 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
     CK(cudaStreamWaitEvent(svx, e->ev_fork, 0));
   }
   const int64_t px_per = (int64_t)3 * c.image * c.image;
-  for (int b0 = 0; b0 < B; b0 += mb) {
-    const int n = (B - b0 < mb) ? (B - b0) : mb;
-    CKR(run_text(e, ids + (int64_t)b0 * S, mask ? mask + (int64_t)b0 * S : nullptr, n, S,
-                 e->pooled_t + (int64_t)b0 * c.text_hidden, stx));
-    CKR(run_vision(e, px + b0 * px_per, n, e->pooled_v + (int64_t)b0 * c.vis_hidden, svx));
+  // enqueue the two towers' chunks alternately so that neither stream starves while the host is still launching
+  for (int bt = 0, bv = 0; bt < B || bv < B;) {
+    if (bt < B) {
+      const int n = std::min(ct, B - bt);
+      CKR(run_text(e, ids + (int64_t)bt * S, mask ? mask + (int64_t)bt * S : nullptr, n, S,
+                   e->pooled_t + (int64_t)bt * c.text_hidden, stx));
+      bt += n;
+    }
+    if (bv < B) {
+      const int n = std::min(cv, B - bv);
+      CKR(run_vision(e, px + bv * px_per, n, e->pooled_v + (int64_t)bv * c.vis_hidden, svx));
+      bv += n;
+    }
   }
   if (two) {
     CK(cudaEventRecord(e->ev_text, stx));
@@ -997,11 +1068,13 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   if (attention_mask) CK(cudaMemcpyAsync(e->d_mask, attention_mask, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_tp, text_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_ip, image_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  int mb = e->opt_micro_batch;
-  if (mb > B) mb = B;
-  CKR(ensure_arenas(e, mb));
+  const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min((int)B, e->opt_micro_batch);
+  const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, e->opt_micro_batch, g_num_sms)
+                                   : std::min((int)B, e->opt_micro_batch);
+  e->last_chunk_text = ct; e->last_chunk_vis = cv;
+  CKR(ensure_arenas(e, ct, cv));
   CKR(ensure_batch(e, B));
-  const int nchunks = (B + mb - 1) / mb;
+  const int nchunks = (B + cv - 1) / cv;
   while ((int)e->ev_chunk.size() < nchunks) {
     cudaEvent_t ev;
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1010,7 +1083,7 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   CK(cudaEventRecord(e->ev_fork, st));
   CK(cudaStreamWaitEvent(e->s_copy, e->ev_fork, 0));
   for (int ci = 0; ci < nchunks; ++ci) {
-    const int b0 = ci * mb, n = (B - b0 < mb) ? (B - b0) : mb;
+    const int b0 = ci * cv, n = std::min(cv, (int)B - b0);
     CK(cudaMemcpyAsync(e->d_px + b0 * px_per, pixel_values + b0 * px_per, (size_t)n * px_per * 4,
                        cudaMemcpyHostToDevice, e->s_copy));
     CK(cudaEventRecord(e->ev_chunk[ci], e->s_copy));
@@ -1020,12 +1093,20 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   CK(cudaStreamWaitEvent(e->s_text, e->ev_fork, 0));
   CK(cudaStreamWaitEvent(e->s_vis, e->ev_fork, 0));
   const int64_t* dmask = attention_mask ? e->d_mask : nullptr;
-  for (int ci = 0; ci < nchunks; ++ci) {
-    const int b0 = ci * mb, n = (B - b0 < mb) ? (B - b0) : mb;
-    CKR(run_text(e, e->d_ids + (int64_t)b0 * S, dmask ? dmask + (int64_t)b0 * S : nullptr, n, S,
-                 e->pooled_t + (int64_t)b0 * c.text_hidden, e->s_text));
-    CK(cudaStreamWaitEvent(e->s_vis, e->ev_chunk[ci], 0));
-    CKR(run_vision(e, e->d_px + b0 * px_per, n, e->pooled_v + (int64_t)b0 * c.vis_hidden, e->s_vis));
+  for (int bt = 0, bv = 0, ci = 0; bt < B || bv < B;) {
+    if (bt < B) {
+      const int n = std::min(ct, (int)B - bt);
+      CKR(run_text(e, e->d_ids + (int64_t)bt * S, dmask ? dmask + (int64_t)bt * S : nullptr, n, S,
+                   e->pooled_t + (int64_t)bt * c.text_hidden, e->s_text));
+      bt += n;
+    }
+    if (bv < B) {
+      const int n = std::min(cv, (int)B - bv);
+      CK(cudaStreamWaitEvent(e->s_vis, e->ev_chunk[ci], 0));
+      CKR(run_vision(e, e->d_px + bv * px_per, n, e->pooled_v + (int64_t)bv * c.vis_hidden, e->s_vis));
+      bv += n;
+      ++ci;
+    }
   }
   CK(cudaEventRecord(e->ev_text, e->s_text));
   CK(cudaEventRecord(e->ev_vis, e->s_vis));
@@ -1099,6 +1180,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
   } else if (n == "debug_feats") h->opt_debug_feats = value != 0;
+  else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else return fail(MMCM_EINVAL, "unknown option '%s'", name);
   return MMCM_OK;
 }

@@ -76,21 +76,23 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // bf16 outputs: 64 columns starting at col0 (two TMEM loads), rows row_base .. row_base+31
+// `bias_smem` = shared-memory address of this chunk's 64 bias values (staged per tile by the warp itself: with
+// ~220 KB of the SM's 228 KB used as shared memory the L1 is a few KB, and per-chunk __ldg's of the bias were L2
+// round trips sitting directly in front of the FADDs -- the top stall of the first profile of this epilogue).
 template <int EPI>
-__device__ __forceinline__ void epi_chunk_bf16(const EpiParams& ep, const uint32_t stage, const int lane,
-                                               const int row_base, const int col0, const int M,
+__device__ __forceinline__ void epi_chunk_bf16(const EpiParams& ep, const uint32_t stage, const uint32_t bias_smem,
+                                               const int lane, const int row_base, const int col0, const int M,
                                                const uint32_t (&r0)[32], const uint32_t (&r1)[32]) {
   uint32_t w[32];
-  const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(i < 4 ? r0[8 * i + j] : r1[8 * (i - 4) + j]);
-    if (ep.bias) {
-      const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
-      v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
-      v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+    {
+      const uint4 ba = lds128(bias_smem + i * 32), bb = lds128(bias_smem + i * 32 + 16);
+      v[0] += __uint_as_float(ba.x); v[1] += __uint_as_float(ba.y); v[2] += __uint_as_float(ba.z); v[3] += __uint_as_float(ba.w);
+      v[4] += __uint_as_float(bb.x); v[5] += __uint_as_float(bb.y); v[6] += __uint_as_float(bb.z); v[7] += __uint_as_float(bb.w);
     }
     if (EPI == EPI_BIAS_ACT_BF16) {
       if (ep.act == ACT_QUICK_GELU) {
@@ -154,12 +156,10 @@ __device__ __forceinline__ void epi_load_addend(const EpiParams& ep, const int l
 template <int EPI>
 __device__ __forceinline__ void epi_chunk_f32(const EpiParams& ep, const uint32_t stage, const int lane,
                                               const int row_base, const int col0, const int M,
-                                              const uint32_t (&r)[32], const float4 (&x)[8]) {
+                                              const uint32_t (&r)[32], const float4 (&x)[8], const float4 bias) {
   float* out = reinterpret_cast<float*>(ep.out);
   const int sub = lane >> 3, c16 = lane & 7;
   const int col = col0 + c16 * 4;
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     if ((lane >> 4) == pass) {
@@ -307,7 +307,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024: 1 KB alignment
+  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;  // per epilogue warp: the bias of its column half
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;  // +1024: 1 KB alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                   // double-buffered accumulator
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
   static constexpr int SCHED_SLOTS = 4;
@@ -445,6 +447,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int e = warp - 4;
     const int lg = e & 3, ch = e >> 2;
     const uint32_t stage_smem = epi_base + e * EPI_STAGE_BYTES;
+    const uint32_t bias_smem = epi_base + C::EPI_WARPS * EPI_STAGE_BYTES + e * C::EPI_BIAS_BYTES;
     constexpr int HALF_N = BLOCK_N / 2;
     int as = 0, slot = 0;
     uint32_t aphase = 0, sphase = 0;
@@ -460,7 +463,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col_base = n_blk * BLOCK_N + ch * HALF_N;
       constexpr bool kF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32);
       float4 xa[8];
-      if (kF32 && row_base < M) epi_load_addend<EPI>(ep, lane, row_base, col_base, M, xa);  // overlaps the MMAs
+      float4 fb[HALF_N / 32];   // fp32 path: this lane's bias for each 32-column chunk
+      // everything the epilogue needs from global memory is requested BEFORE waiting for the accumulator
+      if (kF32) {
+#pragma unroll
+        for (int c = 0; c < HALF_N / 32; ++c)
+          fb[c] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base + c * 32 + (lane & 7) * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_base < M) epi_load_addend<EPI>(ep, lane, row_base, col_base, M, xa);
+      } else {
+#pragma unroll
+        for (int j = lane; j < HALF_N / 4; j += 32) {
+          const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          sts128(bias_smem + j * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+        }
+        __syncwarp();
+      }
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BLOCK_N + ch * HALF_N);
@@ -472,7 +491,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld32(t_row + (uint32_t)(c * 64), r0);
             tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r1);
             tmem_ld_wait();
-            epi_chunk_bf16<EPI>(ep, stage_smem, lane, row_base, col_base + c * 64, M, r0, r1);
+            epi_chunk_bf16<EPI>(ep, stage_smem, bias_smem + c * 256, lane, row_base, col_base + c * 64, M, r0, r1);
           }
         } else {
 #pragma unroll
@@ -482,7 +501,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld32(t_row + (uint32_t)(c * 32), r);
             if (c + 1 < HALF_N / 32) epi_load_addend<EPI>(ep, lane, row_base, col_base + (c + 1) * 32, M, xn);
             tmem_ld_wait();
-            epi_chunk_f32<EPI>(ep, stage_smem, lane, row_base, col_base + c * 32, M, r, xa);
+            epi_chunk_f32<EPI>(ep, stage_smem, lane, row_base, col_base + c * 32, M, r, xa, fb[c]);
             if (c + 1 < HALF_N / 32) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) xa[i] = xn[i];

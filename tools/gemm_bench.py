@@ -14,6 +14,8 @@ from mmcm_b200 import lib as L  # noqa: E402
 
 lib = L.load()
 mb = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+only = sys.argv[2] if len(sys.argv) > 2 else ""
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 SHAPES = []
 for name, T, D, F in (("text", 77, 512, 2048), ("vision", 50, 768, 3072)):
     M = mb * T
@@ -23,6 +25,8 @@ SHAPES.append(("vision.patch", mb * 49, 768, 3072, 3))
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 tot_t = tot_f = 0.0
 for name, M, N, K, epi in SHAPES:
+    if only and only not in name:
+        continue
     nbuf = 4
     A = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
     W = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
@@ -42,7 +46,6 @@ for name, M, N, K, epi in SHAPES:
         run(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 40
     e0.record()
     for i in range(iters):
         run(i)

@@ -112,7 +112,7 @@ MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
 /* CUDA-event time (ms) of the GEMM launches of the last forward when profiling was enabled with
  * mmcm_set_option(h, "time_gemms", 1); also returns their FLOPs. Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
-/* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05, 1 = SIMT validation kernel),
+/* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel),
  * "micro_batch" (upper bound on the samples per internal pass of a tower), "auto_chunk" (1 = pick, per tower, the
  * chunk size <= micro_batch whose GEMM tile counts fill whole waves of the 148 SMs; 0 = use micro_batch as is),
  * "streams" (1 or 2: text/vision towers on separate streams), "debug_feats" (0/1: keep the projected
@@ -128,7 +128,8 @@ MMCM_API const char* mmcm_version(void);
 #define MMCM_EPI_PATCH_F32 3       /* out fp32[(r/P)*T+off+r%P] = acc + bias? + pos[off+r%P] */
 
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): A, W bf16 row-major device pointers (K % 64 == 0, N % 128 == 0).
- * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT validation kernel. act = MMCM_ACT_* for EPI_BIAS_ACT.
+ * impl 0 = tcgen05/TMEM/TMA kernel on CTA pairs (cta_group::2, 256 x BLOCK_N tiles), 1 = SIMT validation kernel,
+ * 2 = tcgen05 single-CTA kernel (128 x BLOCK_N tiles, dynamic tile scheduler). act = MMCM_ACT_* for EPI_BIAS_ACT.
  * For EPI_PATCH: pos fp32 [T,N], P = patches per sample, T = tokens per sample, off = T - P. */
 MMCM_API int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K,
                    int32_t epilogue, int32_t act, void* out, const float* resid, const float* pos,
@@ -140,6 +141,9 @@ MMCM_API int mmcm_layernorm(const float* x, const float* gamma, const float* bet
  * key_valid uint8 [B,T] or NULL; causal 0/1; out bf16 [B*T, D]. A query with no admissible key yields 0. */
 MMCM_API int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B, int32_t T, int32_t heads,
                    int32_t causal, void* out, void* stream);
+/* Dev tool: when device_buffer != NULL, mmcm_gemm_bf16 (impl 0) writes 16 clock64 stamps per CTA into it
+ * (>= 148 * 16 int64); NULL switches tracing off. */
+MMCM_API int mmcm_debug_set_gemm_trace(void* device_buffer);
 /* fp32 -> bf16 with scale (device pointers), used by tests to prepare operands. */
 MMCM_API int mmcm_cast_bf16(const float* src, void* dst, int64_t n, float scale, void* stream);
 

@@ -1,0 +1,267 @@
+// K2 (2-CTA): out[M,N] = epilogue(A[M,K] @ W[N,K]^T) with tcgen05.mma.cta_group::2 -- one 256 x BLOCK_N tile per
+// CTA PAIR (two SMs of one TPC, launched as a 2-CTA cluster).
+//
+// Why: with one CTA per tile the tensor pipe reads A (4 KB) + B (8 KB) from shared memory for every 128-cycle
+// UMMA while TMA writes the same 96 B/cycle back in -- more than the SM's shared-memory bandwidth, which capped the
+// single-CTA kernel at ~59 % tensor-pipe activity (profiles/r01_gemm_v2_*.txt).  In pair mode each CTA stages its own
+// 128 rows of A and only HALF of the B tile; the pair's UMMA (M = 256) reads both halves, so shared-memory and L2
+// traffic per FLOP drop by a third and the ring holds 6 stages instead of 4.
+//
+// Protocol (rank 0 = leader):
+//   * both producers load their halves into their own smem and complete_tx on the LEADER's full barrier
+//     (cp.async.bulk.tensor ... .cta_group::2, barrier address with the peer bit cleared); the leader's producer
+//     arms it with expect_tx(2 x stage bytes)
+//   * the leader's MMA warp issues tcgen05.mma.cta_group::2 and releases ring slots / publishes accumulators with
+//     tcgen05.commit ... multicast::cluster to the same barrier offset in BOTH CTAs
+//   * each CTA's 8 epilogue warps drain that CTA's 128 accumulator rows from its own TMEM (same coalesced epilogue
+//     as the single-CTA kernel) and arrive on the leader's tmem-empty barrier (remote mbarrier.arrive)
+//   * tiles are assigned round-robin to the pairs (static: the pair shares no scheduler state)
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace mmcm {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair leader)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the pair leader's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t holder_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs of this thread have retired) on `bar` in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static constexpr int BLOCK_M = 256;           // per pair; 128 rows per CTA
+  static constexpr int BLOCK_K = 64;
+  static constexpr int UMMA_K = 16;
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;   // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BLOCK_N>::THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const EpiParams ep, const int M, const int N, const int K) {
+  using C = Gemm2Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[C::STAGES];    // used in the leader only
+  __shared__ __align__(8) uint64_t bar_empty[C::STAGES];   // one copy per CTA (multicast commit)
+  __shared__ __align__(8) uint64_t bar_tfull[2];           // one copy per CTA (multicast commit)
+  __shared__ __align__(8) uint64_t bar_tempty[2];          // used in the leader only: 2 x EPI_WARPS arrivals
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_stamp(ep, 0);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
+
+  const int tiles_n = N / BLOCK_N;
+  const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = K / C::BLOCK_K;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 2 * C::EPI_WARPS);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_holder), C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote traffic
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  if (threadIdx.x == 0) trace_stamp(ep, 1);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int a_row = m_blk * C::BLOCK_M + (int)rank * 128;
+      const int b_row = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          if (leader) mbar_expect_tx(full, 2 * C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+          tma_load_2d_pair(&tmap_a, full, sa, kb * C::BLOCK_K, a_row);
+          tma_load_2d_pair(&tmap_b, full, sa + C::A_BYTES, kb * C::BLOCK_K, b_row);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader only) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(C::BLOCK_M, BLOCK_N);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);   // both CTAs' epilogues have drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          if (kb == 0 && tile == pair) trace_stamp(ep, 2);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k)
+            umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_pair(smem_u32(&bar_empty[stage]));
+          if (kb == num_kb - 1) {
+            umma_commit_pair(smem_u32(&bar_tfull[as]));
+            if (tile == pair) trace_stamp(ep, 3);
+            trace_stamp(ep, 6);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====================
+    const int e = warp - 4;
+    const int lg = e & 3, ch = e >> 2;
+    const uint32_t stage_smem = epi_base + e * EPI_STAGE_BYTES;
+    const uint32_t bias_smem = epi_base + C::EPI_WARPS * EPI_STAGE_BYTES + e * C::EPI_BIAS_BYTES;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr bool kF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int row_base = m_blk * C::BLOCK_M + (int)rank * 128 + lg * 32;
+      const int col_base = n_blk * BLOCK_N + ch * HALF_N;
+      float4 xa[8];
+      float4 fb[HALF_N / 32];
+      if (kF32) {
+#pragma unroll
+        for (int c = 0; c < HALF_N / 32; ++c)
+          fb[c] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base + c * 32 + (lane & 7) * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_base < M) epi_load_addend<EPI>(ep, lane, row_base, col_base, M, xa);
+      } else {
+#pragma unroll
+        for (int j = lane; j < HALF_N / 4; j += 32) {
+          const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          sts128(bias_smem + j * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+        }
+        __syncwarp();
+      }
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+      tc_fence_after();
+      if (e == 0 && lane == 0) { if (tile == pair) trace_stamp(ep, 4); trace_stamp(ep, 7); }
+      const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BLOCK_N + ch * HALF_N);
+      if (row_base < M) {
+        if (!kF32) {
+#pragma unroll 1
+          for (int c = 0; c < HALF_N / 64; ++c) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + (uint32_t)(c * 64), r0);
+            tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r1);
+            tmem_ld_wait();
+            epi_chunk_bf16<EPI>(ep, stage_smem, bias_smem + c * 256, lane, row_base, col_base + c * 64, M, r0, r1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < HALF_N / 32; ++c) {
+            uint32_t r[32];
+            float4 xn[8];
+            tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            if (c + 1 < HALF_N / 32) epi_load_addend<EPI>(ep, lane, row_base, col_base + (c + 1) * 32, M, xn);
+            tmem_ld_wait();
+            epi_chunk_f32<EPI>(ep, stage_smem, lane, row_base, col_base + c * 32, M, r, xa, fb[c]);
+            if (c + 1 < HALF_N / 32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xa[i] = xn[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[as]));
+      if (e == 0 && lane == 0) { if (tile == pair) trace_stamp(ep, 5); trace_stamp(ep, 8); }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  if (threadIdx.x == 0) trace_stamp(ep, 9);
+  tc_fence_before();
+  cluster_sync_all();   // nobody frees TMEM / exits while the peer may still read its smem or write its TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace mmcm

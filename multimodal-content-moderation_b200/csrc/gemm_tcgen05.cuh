@@ -36,7 +36,14 @@ struct EpiParams {
   int ldo;             // row pitch of out / resid in elements
   int P, T;            // EPI_PATCH_F32: patches per sample, tokens per sample (T-P leading class rows)
   int act;             // Act for EPI_BIAS_ACT_BF16
+  long long* trace;    // dev tool (mmcm_debug_set_gemm_trace): per-CTA clock64 stamps, 16 slots per CTA; else nullptr
 };
+
+// trace slots: 0 entry, 1 prologue done, 2 first operands landed, 3 MMAs of tile 0 issued, 4 accumulator 0 ready,
+// 5 epilogue of tile 0 done, 6 MMAs of the last tile issued, 7 last accumulator ready, 8 last epilogue done, 9 exit
+__device__ __forceinline__ void trace_stamp(const EpiParams& ep, int slot) {
+  if (ep.trace) ep.trace[(size_t)blockIdx.x * 16 + slot] = clock64();
+}
 
 // ------------------------------------------------------------------------------------------------
 // epilogue math, shared by the tcgen05 kernel (32-column chunks) and the SIMT validation kernel

@@ -29,6 +29,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "gemm2_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "heads.cuh"
 #include "rowwise.cuh"
@@ -178,6 +179,21 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
   return MMCM_OK;
 }
 
+template <int BN, int EPI>
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, int M, int N, int K,
+                          cudaStream_t st) {
+  using C = Gemm2Cfg<BN>;
+  auto kern = gemm2_tcgen05_kernel<BN, EPI>;
+  static AttrOnce once;
+  if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
+  const int pairs = g_num_sms / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);   // __cluster_dims__(2,1,1) on the kernel
+  CK(cudaGetLastError());
+  return MMCM_OK;
+}
+
 template <int EPI>
 static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, const EpiParams& ep, int impl,
                            cudaStream_t st) {
@@ -191,6 +207,11 @@ static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, co
   const int BN = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   CKR(get_tmap(&ta, A, M, K, 128, false));
+  if (impl == 0) {  // CTA-pair kernel: every CTA stages half of the B tile
+    CKR(get_tmap(&tb, W, N, K, BN / 2, true));
+    if (BN == 256) return launch_tc_pair<256, EPI>(ta, tb, ep, M, N, K, st);
+    return launch_tc_pair<128, EPI>(ta, tb, ep, M, N, K, st);
+  }
   CKR(get_tmap(&tb, W, N, K, BN, true));
   if (BN == 256) return launch_tc<256, EPI>(ta, tb, ep, M, N, K, st);
   return launch_tc<128, EPI>(ta, tb, ep, M, N, K, st);
@@ -1171,7 +1192,8 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "time_gemms") h->stats.time_gemms = value != 0;
   else if (n == "gemm_impl") {
-    if (value != 0 && value != 1) return fail(MMCM_EINVAL, "gemm_impl must be 0 (tcgen05) or 1 (SIMT validation)");
+    if (value < 0 || value > 2)
+      return fail(MMCM_EINVAL, "gemm_impl must be 0 (tcgen05 CTA pair), 1 (SIMT validation) or 2 (tcgen05 single CTA)");
     h->opt_gemm_impl = (int)value;
   } else if (n == "micro_batch") {
     if (value < 1 || value > 65536) return fail(MMCM_EINVAL, "micro_batch out of range");
@@ -1185,6 +1207,13 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   return MMCM_OK;
 }
 
+// dev tool: per-CTA clock64 stamps of the CTA-pair GEMM (16 slots per CTA; see trace_stamp in gemm_tcgen05.cuh)
+static long long* g_gemm_trace = nullptr;
+int mmcm_debug_set_gemm_trace(void* device_buffer) {
+  g_gemm_trace = reinterpret_cast<long long*>(device_buffer);
+  return MMCM_OK;
+}
+
 // ---------------------------------------------------------------------------------- stand-alone kernels
 int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                    int32_t act, void* out, const float* resid, const float* pos, int32_t P, int32_t T, int32_t impl,
@@ -1193,6 +1222,7 @@ int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, i
   if (epilogue == EPI_PATCH_F32 && (!pos || P <= 0 || T < P)) return fail(MMCM_EINVAL, "patch epilogue needs pos, P, T");
   EpiParams ep{};
   ep.bias = bias; ep.out = out; ep.resid = resid; ep.pos = pos; ep.ldo = N; ep.P = P; ep.T = T; ep.act = act;
+  ep.trace = g_gemm_trace;
   return launch_gemm(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(W), M, N, K, epilogue, ep, impl,
                      reinterpret_cast<cudaStream_t>(stream), nullptr);
 }

@@ -51,6 +51,7 @@ _SIGS = {
     "mmcm_layernorm": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mmcm_cast_bf16": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),
+    "mmcm_debug_set_gemm_trace": (C.c_int, [_P]),
 }
 
 _lib: Optional[C.CDLL] = None

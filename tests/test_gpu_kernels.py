@@ -37,7 +37,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])   # 0 = tcgen05 CTA pair, 1 = SIMT validation, 2 = tcgen05 single CTA
 def test_gemm_bias_bf16(lib, M, N, K, impl):
     if impl == 1 and M * N * K > 3e10:
         pytest.skip("SIMT validation kernel only on small shapes")
@@ -56,8 +56,9 @@ def test_gemm_bias_bf16(lib, M, N, K, impl):
     assert torch.isfinite(out.float()).all()
 
 
+@pytest.mark.parametrize("impl", [0, 2])
 @pytest.mark.parametrize("act", [1, 2])
-def test_gemm_bias_act(lib, act):
+def test_gemm_bias_act(lib, act, impl):
     M, N, K = 1000, 3072, 768
     g = torch.Generator(device="cuda").manual_seed(act)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -65,7 +66,7 @@ def test_gemm_bias_act(lib, act):
     bias = torch.randn(N, device="cuda", generator=g)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 1, act, out.data_ptr(), None, None,
-                              0, 0, 0, _stream()))
+                              0, 0, impl, _stream()))
     torch.cuda.synchronize()
     pre = A.float() @ W.float().t() + bias
     ref = _quick_gelu(pre) if act == 1 else torch.nn.functional.gelu(pre, approximate="tanh")
@@ -73,7 +74,8 @@ def test_gemm_bias_act(lib, act):
     assert (err <= 1e-2 * ref.abs() + 1e-2).all(), f"max err {err.max().item()}"
 
 
-def test_gemm_bias_residual_in_place(lib):
+@pytest.mark.parametrize("impl", [0, 2])
+def test_gemm_bias_residual_in_place(lib, impl):
     M, N, K = 777, 768, 3072
     g = torch.Generator(device="cuda").manual_seed(11)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -82,12 +84,13 @@ def test_gemm_bias_residual_in_place(lib):
     x = torch.randn(M, N, device="cuda", generator=g)
     ref = x + A.float() @ W.float().t() + bias
     _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 2, 0, x.data_ptr(), x.data_ptr(),
-                              None, 0, 0, 0, _stream()))
+                              None, 0, 0, impl, _stream()))
     torch.cuda.synchronize()
     assert (x - ref).abs().max().item() < 2e-3   # fp32 out: summation order only
 
 
-def test_gemm_patch_epilogue(lib):
+@pytest.mark.parametrize("impl", [0, 2])
+def test_gemm_patch_epilogue(lib, impl):
     """rows of the im2col GEMM land at token 1..49 of each sample with the position embedding added."""
     Bn, P, T, N, K = 5, 49, 50, 768, 3072
     M = Bn * P
@@ -97,7 +100,7 @@ def test_gemm_patch_epilogue(lib):
     pos = torch.randn(T, N, device="cuda", generator=g)
     out = torch.full((Bn * T, N), 123.0, device="cuda")
     _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), None, M, N, K, 3, 0, out.data_ptr(), None, pos.data_ptr(),
-                              P, T, 0, _stream()))
+                              P, T, impl, _stream()))
     torch.cuda.synchronize()
     ref = (A.float() @ W.float().t()).view(Bn, P, N) + pos[1:][None]
     o = out.view(Bn, T, N)

@@ -16,6 +16,7 @@ lib = L.load()
 mb = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 only = sys.argv[2] if len(sys.argv) > 2 else ""
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+impl = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 SHAPES = []
 for name, T, D, F in (("text", 77, 512, 2048), ("vision", 50, 768, 3072)):
     M = mb * T
@@ -27,7 +28,7 @@ tot_t = tot_f = 0.0
 for name, M, N, K, epi in SHAPES:
     if only and only not in name:
         continue
-    nbuf = 4
+    nbuf = int(os.environ.get("NBUF", "4"))
     A = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
     W = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
     bias = torch.randn(N, device="cuda")
@@ -41,7 +42,7 @@ for name, M, N, K, epi in SHAPES:
         o = out[i % nbuf]
         L.check(lib.mmcm_gemm_bf16(A[i % nbuf].data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, epi, 1, o.data_ptr(),
                                    o.data_ptr() if epi == 2 else None, pos.data_ptr() if epi == 3 else None,
-                                   49 if epi == 3 else 0, 50 if epi == 3 else 0, 0, st))
+                                   49 if epi == 3 else 0, 50 if epi == 3 else 0, impl, st))
     for i in range(5):
         run(i)
     torch.cuda.synchronize()

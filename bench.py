@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="samples per step per GPU")
     ap.add_argument("--micro-batch", type=int, default=0, help="engine micro-batch (0 = library default)")
     ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch on/off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -201,6 +202,7 @@ def main():
     if args.micro_batch:
         m.set_option("micro_batch", args.micro_batch)
     m.set_option("streams", args.streams)
+    m.set_option("pdl", args.pdl)
     eng = m._ensure_engine(local_rank)
 
     B = args.batch
@@ -302,7 +304,7 @@ def main():
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB/step/GPU vs 126 MB)",
-                           "micro_batch": args.micro_batch or "library default", "streams": args.streams,
+                           "micro_batch": args.micro_batch or "library default", "streams": args.streams, "pdl": args.pdl,
                            "algorithmic_gflop_per_sample": flops["total"] / 1e9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu, "parity": parity}

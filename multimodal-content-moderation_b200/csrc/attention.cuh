@@ -54,6 +54,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   __nv_bfloat16* Vs = Ks + TPAD * ATT_LD;
   uint8_t* kvs = reinterpret_cast<uint8_t*>(Vs + TPAD * ATT_LD);
 
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
   const int T = seq_len ? seq_len[b] : T_fixed;
   const int row0 = seq_start ? seq_start[b] : b * T_fixed;
@@ -62,24 +64,41 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int q0 = blockIdx.z * QW * 16;   // first query row of this CTA
   if (q0 >= T) return;                   // whole CTA is padding (uniform exit before any barrier)
 
-  // ---- stage K, V (all keys) and Q (own rows) of this (sample, head): 8 x 16-byte chunks per row; zero the padding
-  for (int idx = tid; idx < TPAD * 16; idx += nthr) {
-    const int t = idx >> 4, c = idx & 15;
-    const int mat = 1 + (c >> 3), ch = c & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (t < T) {
-      const __nv_bfloat16* src = qkv + (size_t)(row0 + t) * ld_qkv + mat * D + h * ATT_DH + ch * 8;
-      v = *reinterpret_cast<const uint4*>(src);
+  // ---- stage K, V (all keys) and Q (own rows) of this (sample, head): 8 x 16-byte chunks per row; zero the padding.
+  // All global loads of a thread are issued before its first shared-memory store (fully unrolled, independent),
+  // so a CTA has its whole working set in flight at once instead of one 16-byte load per thread at a time.
+  {
+    constexpr int NTHR = QW * 32;
+    constexpr int KV_CHUNKS = TPAD * 16;
+    constexpr int KV_ITERS = (KV_CHUNKS + NTHR - 1) / NTHR;
+    uint4 kv[KV_ITERS], qv[4];
+#pragma unroll
+    for (int i = 0; i < KV_ITERS; ++i) {
+      const int idx = tid + i * NTHR;
+      const int t = idx >> 4, c = idx & 15;
+      kv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < KV_CHUNKS && t < T)
+        kv[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + t) * ld_qkv + (1 + (c >> 3)) * D + h * ATT_DH +
+                                                     (c & 7) * 8));
     }
-    __nv_bfloat16* dst = (mat == 1 ? Ks : Vs) + t * ATT_LD + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
-  }
-  for (int idx = tid; idx < QW * 16 * 8; idx += nthr) {
-    const int tl = idx >> 3, ch = idx & 7;
-    const int t = q0 + tl;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (t < T) v = *reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + t) * ld_qkv + h * ATT_DH + ch * 8);
-    *reinterpret_cast<uint4*>(Qs + tl * ATT_LD + ch * 8) = v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // QW*16 rows x 8 chunks = 4 per thread
+      const int idx = tid + i * NTHR;
+      const int t = q0 + (idx >> 3);
+      qv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (t < T) qv[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + t) * ld_qkv + h * ATT_DH + (idx & 7) * 8));
+    }
+#pragma unroll
+    for (int i = 0; i < KV_ITERS; ++i) {
+      const int idx = tid + i * NTHR;
+      const int t = idx >> 4, c = idx & 15;
+      if (idx < KV_CHUNKS) *reinterpret_cast<uint4*>(((c >> 3) == 0 ? Ks : Vs) + t * ATT_LD + (c & 7) * 8) = kv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * NTHR;
+      *reinterpret_cast<uint4*>(Qs + (idx >> 3) * ATT_LD + (idx & 7) * 8) = qv[i];
+    }
   }
   for (int t = tid; t < TPAD; t += nthr) {
     uint8_t ok = (t < T) ? 1 : 0;
@@ -210,6 +229,8 @@ map_attention_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restri
   __shared__ float sc[MAP_MAXT];
   __shared__ float red[4];
   __shared__ float acc[4][ATT_DH];
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* base = kv + (size_t)b * T * 2 * D + h * ATT_DH;
@@ -256,6 +277,7 @@ map_attention_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restri
 __global__ void probe_query_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                    const float* __restrict__ probe, float* __restrict__ q, const int D,
                                    const float scale) {
+  pdl_wait();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= D) return;

@@ -14,6 +14,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (PDL): every kernel of the forward is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may become resident while the previous kernel of
+// the stream is still draining.  pdl_wait() blocks until all prerequisite grids have completed and their memory is
+// visible -- it must precede the first global access that depends on them; pdl_trigger() lets the NEXT kernel start
+// launching.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

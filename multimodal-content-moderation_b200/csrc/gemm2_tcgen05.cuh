@@ -130,6 +130,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
   if (threadIdx.x == 0) trace_stamp(ep, 1);
+  // PDL: barrier init, TMEM allocation and the cluster handshake above overlapped the previous kernel's tail
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

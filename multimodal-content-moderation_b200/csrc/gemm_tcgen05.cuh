@@ -373,6 +373,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  // PDL: everything above overlapped the previous kernel's tail; its outputs (A, the residual) are safe to read now
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== tile scheduler + TMA producer =====================
@@ -542,6 +545,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __nv_bfloat16* __r
                                                         const int M, const int N, const int K) {
   __shared__ float As[32][33];
   __shared__ float Ws[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};

@@ -14,7 +14,7 @@
 namespace mmcm {
 
 constexpr int HEAD_SB = 8;        // samples per CTA
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 512;
 constexpr int HEAD_MAXD = 768;    // widest tower feature
 
 enum HeadAct : int { HA_NONE = 0, HA_TANH = 1, HA_SIGMOID = 2, HA_GELU = 3 };
@@ -45,30 +45,61 @@ __device__ __forceinline__ float head_act(float v, int act) {
 }
 
 // ys[s][n] = act(sum_k xs[s][k] * W[n][k] + bias[n]) for s < HEAD_SB, n < N.  K % 4 == 0, W rows 16-B aligned.
+// A warp produces HEAD_NB = 4 output columns per pass: every 16-byte slice of x that is read from shared memory is
+// used for 4 weight rows (the first version re-read x for every row and was shared-memory bound, 1.1 ms per 1024
+// samples), the weight rows are streamed with coalesced 128-bit loads, and the 8 x 4 = 32 partial sums per lane are
+// reduced across the warp with a transposing butterfly (31 shuffles instead of 160) that leaves (sample, column) =
+// (lane / 4, lane % 4) in lane `lane`.
+constexpr int HEAD_NB = 4;
+static_assert(HEAD_SB * HEAD_NB == 32, "the butterfly below assumes 32 partial sums per lane");
+
 __device__ __forceinline__ void block_linear(const float* __restrict__ W, const float* __restrict__ bias, const int N,
                                              const int K, const float* xs, const int ldx, float* ys,
                                              const int ldy, const int act) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < N; n += nw) {
-    const float4* wr = reinterpret_cast<const float4*>(W + (size_t)n * K);
-    float acc[HEAD_SB];
+  const int K4 = K >> 2;
+  for (int n0 = warp * HEAD_NB; n0 < N; n0 += nw * HEAD_NB) {
+    float v[32];
 #pragma unroll
-    for (int s = 0; s < HEAD_SB; ++s) acc[s] = 0.f;
-    for (int k4 = lane; k4 < (K >> 2); k4 += 32) {
-      const float4 w = __ldg(wr + k4);
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    const float4* wr[HEAD_NB];
 #pragma unroll
-      for (int s = 0; s < HEAD_SB; ++s) {
-        const float4 x = *reinterpret_cast<const float4*>(xs + s * ldx + 4 * k4);
-        acc[s] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[s]))));
+    for (int j = 0; j < HEAD_NB; ++j) wr[j] = reinterpret_cast<const float4*>(W + (size_t)min(n0 + j, N - 1) * K);
+    // two k-slices per iteration: 8 independent 128-bit weight loads in flight per lane (the kernel is latency bound:
+    // one CTA per SM, so bytes in flight = warps x loads per lane x 512 B)
+    for (int k4 = lane; k4 < K4; k4 += 64) {
+      float4 w[2][HEAD_NB];
+      const bool second = (k4 + 32) < K4;
+#pragma unroll
+      for (int j = 0; j < HEAD_NB; ++j) {
+        w[0][j] = __ldg(wr[j] + k4);
+        w[1][j] = second ? __ldg(wr[j] + k4 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !second) break;
+#pragma unroll
+        for (int s = 0; s < HEAD_SB; ++s) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + s * ldx + 4 * (k4 + 32 * u));
+#pragma unroll
+          for (int j = 0; j < HEAD_NB; ++j)
+            v[s * HEAD_NB + j] = fmaf(w[u][j].x, x.x, fmaf(w[u][j].y, x.y, fmaf(w[u][j].z, x.z, fmaf(w[u][j].w, x.w, v[s * HEAD_NB + j]))));
+        }
       }
     }
-    float mine = 0.f;
+    // transposing butterfly: after the step with offset `off`, a lane keeps the half of its values selected by its bit
 #pragma unroll
-    for (int s = 0; s < HEAD_SB; ++s) {
-      const float r = warp_sum(acc[s]);
-      if (lane == s) mine = r;
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? v[i] : v[i + off];
+        const float keep = upper ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
     }
-    if (lane < HEAD_SB) ys[lane * ldy + n] = head_act(mine + (bias ? __ldg(bias + n) : 0.f), act);
+    const int s = lane / HEAD_NB, j = lane % HEAD_NB;
+    if (n0 + j < N) ys[s * ldy + n0 + j] = head_act(v[0] + (bias ? __ldg(bias + n0 + j) : 0.f), act);
   }
 }
 
@@ -94,6 +125,8 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
             float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ feat_t_out,
             float* __restrict__ feat_v_out) {
   extern __shared__ __align__(16) float hs[];
+  pdl_trigger();
+  pdl_wait();
   const int fd = w.fd;
   const int ldf = 5 * fd;
   float* bufA = hs;                              // [SB][HEAD_MAXD]

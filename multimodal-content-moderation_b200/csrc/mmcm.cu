@@ -73,6 +73,24 @@ struct AttrOnce {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ launches
+// Every kernel goes through launch_k: cudaLaunchKernelEx with programmatic stream serialization (PDL), see common.cuh.
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ TMA maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -174,7 +192,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   int* sched = nullptr;
   CKR(get_sched(st, &sched));
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K, sched);
+  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, ep, M, N, K, sched));
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -189,7 +207,7 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
   const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
   const int pairs = g_num_sms / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);   // __cluster_dims__(2,1,1) on the kernel
+  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, ep, M, N, K));   // __cluster_dims__(2,1,1) on the kernel
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -199,7 +217,7 @@ static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, co
                            cudaStream_t st) {
   if (impl == 1) {
     dim3 grid(N / 32, (M + 31) / 32);
-    gemm_simt_kernel<EPI><<<grid, 256, 0, st>>>(A, W, ep, M, N, K);
+    CK(launch_k(gemm_simt_kernel<EPI>, dim3(grid), dim3(256), 0, st, A, W, ep, M, N, K));
     CK(cudaGetLastError());
     return MMCM_OK;
   }
@@ -253,9 +271,9 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
                             const int* gather, bf16* out_bf16, float* out_f32, cudaStream_t st, LaunchStats* stats) {
   if (rows <= 0) return MMCM_OK;
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
-  if (D == 512) layernorm_kernel<512><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
-  else if (D == 768) layernorm_kernel<768><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
-  else if (D == 1024) layernorm_kernel<1024><<<blocks, 256, 0, st>>>(x, g, b, eps, rows, gather, out_bf16, out_f32);
+  if (D == 512) CK(launch_k(layernorm_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
+  else if (D == 768) CK(launch_k(layernorm_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
+  else if (D == 1024) CK(launch_k(layernorm_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
   else return fail(MMCM_EINVAL, "layernorm: unsupported width %d (512, 768, 1024)", D);
   CK(cudaGetLastError());
   if (stats) stats->launches++;
@@ -271,7 +289,7 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int qblocks = (TPAD / 16 + QW - 1) / QW;
   dim3 grid(heads, B, qblocks);
-  kern<<<grid, QW * 32, smem, st>>>(qkv, out, kvalid, nullptr, nullptr, T, heads * ATT_DH, causal, T);
+  CK(launch_k(kern, dim3(grid), dim3(QW * 32), smem, st, qkv, out, kvalid, nullptr, nullptr, T, heads * ATT_DH, causal, T));
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -311,6 +329,7 @@ struct Slot {
 
 __global__ void copy2d_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t rows, int64_t cols,
                               int64_t src_pitch, int64_t dst_pitch, int kind, float scale) {
+  pdl_wait();
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
@@ -383,7 +402,7 @@ struct mmcm_handle_s {
   cudaEvent_t ev_fork = nullptr, ev_text = nullptr, ev_vis = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
   // options
-  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 256, opt_debug_feats = 0, opt_auto_chunk = 1;
+  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 512, opt_debug_feats = 0, opt_auto_chunk = 1;
   int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
 };
@@ -678,14 +697,15 @@ static int ensure_arenas(Eng* e, int mbt, int mbv) {
 // cycles of the whole batch: rounds * (k-blocks * 512 + epilogue) per GEMM + a fixed cost per launch.
 static double chunk_cost(const TowerW& t, int T, int n, int sms) {
   if (n <= 0) return 0.0;
-  const double mt = std::ceil((double)n * T / 128.0);
+  const double mt = std::ceil((double)n * T / 256.0);   // CTA-pair tiles: 256 rows
+  const double units = sms / 2;                         // pairs
   auto gemm = [&](int N, int K) {
     const int bn = (N % 256 == 0) ? 256 : 128;
-    const double rounds = std::ceil(mt * (N / bn) / (double)sms);
-    return rounds * ((K / 64) * 512.0 * bn / 256.0 + 2500.0) + 6000.0;
+    const double rounds = std::ceil(mt * (N / bn) / units);
+    return rounds * ((K / 64) * 620.0 * bn / 256.0 + 5000.0) + 12000.0;
   };
   const double layer = gemm(3 * t.D, t.D) + gemm(t.D, t.D) + gemm(t.F, t.D) + gemm(t.D, t.F) +
-                       3 * 6000.0 /* LN, LN, attention launches */ + 3.0 * n * T * t.D / 148.0 / 64.0;
+                       3 * 8000.0 /* LN, LN, attention launches */ + 3.0 * n * T * t.D / 148.0 / 32.0;
   return layer * t.L;
 }
 static int choose_chunk(const TowerW& t, int T, int B, int cap, int sms) {
@@ -755,11 +775,11 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
   const int blocks = (rows + 7) / 8;
   const int eos = clip ? c.eos_id : -1;
   if (t.D == 512)
-    text_embed_kernel<512><<<blocks, 256, 0, st>>>(ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
-                                                   a.pool_row, e->key_valid);
+    CK(launch_k(text_embed_kernel<512>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                                                   a.pool_row, e->key_valid));
   else if (t.D == 768)
-    text_embed_kernel<768><<<blocks, 256, 0, st>>>(ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
-                                                   a.pool_row, e->key_valid);
+    CK(launch_k(text_embed_kernel<768>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                                                   a.pool_row, e->key_valid));
   else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
   CK(cudaGetLastError());
   e->stats.launches++;
@@ -782,7 +802,7 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
   {
     const int64_t chunks = (int64_t)n * P * (Kp / 8);
     const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
-    im2col_kernel<<<blocks, 256, 0, st>>>(px, e->im2col, n, c.image, c.patch);
+    CK(launch_k(im2col_kernel, dim3(blocks), dim3(256), 0, st, px, e->im2col, n, c.image, c.patch));
     CK(cudaGetLastError());
     S->launches++;
   }
@@ -790,14 +810,14 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
   ep.bias = e->bpatch; ep.out = a.x; ep.pos = e->vpos_emb; ep.ldo = D; ep.P = P; ep.T = T;
   CKR(launch_gemm(e->im2col, e->wpatch, n * P, D, Kp, EPI_PATCH_F32, ep, e->opt_gemm_impl, st, S));
   if (clip) {
-    cls_rows_kernel<<<(n * D + 255) / 256, 256, 0, st>>>(e->cls_emb, e->vpos_emb, a.x, n, T, D);
+    CK(launch_k(cls_rows_kernel, dim3((n * D + 255) / 256), dim3(256), 0, st, e->cls_emb, e->vpos_emb, a.x, n, T, D));
     CK(cudaGetLastError());
     S->launches++;
     CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
   }
   CKR(run_layers(e, t, a, rows, n, T, nullptr, 0, st));
   if (clip) {
-    fill_pool_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.pool_row, n, T, 0);
+    CK(launch_k(fill_pool_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a.pool_row, n, T, 0));
     CK(cudaGetLastError());
     S->launches++;
     CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S));
@@ -809,7 +829,7 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
     ep.bias = e->map_bkv; ep.out = e->map_kv; ep.ldo = 2 * D;
     CKR(launch_gemm(a.h, e->map_wkv, rows, 2 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
     if (T > MAP_MAXT) return fail(MMCM_EINVAL, "MAP head: %d tokens > %d", T, MAP_MAXT);
-    map_attention_kernel<<<dim3(t.H, n), 128, 0, st>>>(e->map_kv, e->map_q, e->map_att, T, D);
+    CK(launch_k(map_attention_kernel, dim3(dim3(t.H, n)), dim3(128), 0, st, e->map_kv, e->map_q, e->map_att, T, D));
     CK(cudaGetLastError());
     S->launches++;
     ep = EpiParams{};
@@ -833,8 +853,8 @@ static int run_head(Eng* e, const float* tp, const float* ip, int B, float* logi
   if (once.need()) CK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(MMCM_EINVAL, "head: fusion_dim %d needs too much shared memory", e->cfg.fusion_dim);
   const bool dbg = e->opt_debug_feats && e->cfg.head == MMCM_HEAD_FUSION;
-  head_kernel<<<(B + HEAD_SB - 1) / HEAD_SB, HEAD_THREADS, smem, st>>>(
-      e->hw, e->pooled_t, e->pooled_v, tp, ip, B, logits, probs, dbg ? e->feat_t : nullptr, dbg ? e->feat_v : nullptr);
+  CK(launch_k(head_kernel, dim3((B + HEAD_SB - 1) / HEAD_SB), dim3(HEAD_THREADS), smem, st, 
+      e->hw, e->pooled_t, e->pooled_v, tp, ip, B, logits, probs, dbg ? e->feat_t : nullptr, dbg ? e->feat_v : nullptr));
   CK(cudaGetLastError());
   e->stats.launches++;
   return MMCM_OK;
@@ -1019,7 +1039,7 @@ int mmcm_load_weight(mmcm_handle h, const char* key, const float* src, int64_t n
     const int64_t total = p.rows * p.cols;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    copy2d_kernel<<<blocks, 256>>>(dsrc + p.src_off, p.dst, p.rows, p.cols, p.src_pitch, p.dst_pitch, p.kind, p.scale);
+    CK(launch_k(copy2d_kernel, dim3(blocks), dim3(256), 0, nullptr, dsrc + p.src_off, p.dst, p.rows, p.cols, p.src_pitch, p.dst_pitch, p.kind, p.scale));
   }
   cudaError_t ce = cudaDeviceSynchronize();
   if (stage) cudaFree(stage);
@@ -1042,7 +1062,7 @@ int mmcm_finalize_weights(mmcm_handle h) {
   if (missing) return fail(MMCM_ESTATE, "%d weight tensor(s) missing, e.g. '%s'", missing, first.c_str());
   if (h->cfg.backend == MMCM_BACKEND_SIGLIP) {
     const int D = h->cfg.vis_hidden;
-    probe_query_kernel<<<(D + 7) / 8, 256>>>(h->map_inw, h->map_inb, h->map_probe, h->map_q, D, 1.0f / sqrtf((float)ATT_DH));
+    CK(launch_k(probe_query_kernel, dim3((D + 7) / 8), dim3(256), 0, nullptr, h->map_inw, h->map_inb, h->map_probe, h->map_q, D, 1.0f / sqrtf((float)ATT_DH)));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
   }
@@ -1201,7 +1221,8 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "streams") {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
-  } else if (n == "debug_feats") h->opt_debug_feats = value != 0;
+  } else if (n == "pdl") g_pdl = value != 0;   // process-wide: programmatic dependent launch on/off
+  else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else return fail(MMCM_EINVAL, "unknown option '%s'", name);
   return MMCM_OK;
@@ -1247,8 +1268,8 @@ int mmcm_cast_bf16(const float* src, void* dst, int64_t n, float scale, void* st
   if (n <= 0) return MMCM_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cast_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst),
-                                                                              (size_t)n, scale);
+  CK(launch_k(cast_bf16_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), src, reinterpret_cast<bf16*>(dst),
+                                                                              (size_t)n, scale));
   CK(cudaGetLastError());
   return MMCM_OK;
 }

@@ -21,6 +21,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  const float eps, const int rows, const int* __restrict__ gather,
                  __nv_bfloat16* __restrict__ out_bf16, float* out_f32) {
   constexpr int V = D / 128;  // float4 per lane
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -78,6 +80,8 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
                   const int vocab, const int eos_id, float* __restrict__ x, int* __restrict__ pool_row,
                   uint8_t* __restrict__ key_valid) {
   constexpr int V = D / 128;
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * S) return;
@@ -135,6 +139,8 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ A, const int B, const int img,
               const int p) {
+  pdl_trigger();
+  pdl_wait();
   const int G = img / p;
   const int K = 3 * p * p;
   const int chunks_per_row = K / 8;
@@ -160,6 +166,8 @@ im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ A, const
 // CLIP class-token rows: x[b*T + 0, :] = class_embedding + position_embedding[0]   (HF clip :212-217)
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                 const int B, const int T, const int D) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
@@ -168,6 +176,8 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 
 // pool_row[b] = b*T + t0  (vision CLS row)
 __global__ void fill_pool_rows_kernel(int* __restrict__ pool_row, const int B, const int T, const int t0) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) pool_row[b] = b * T + t0;
 }
@@ -175,6 +185,7 @@ __global__ void fill_pool_rows_kernel(int* __restrict__ pool_row, const int B, c
 // fp32 -> bf16 (weights repack; `scale` folds dh^-1/2 into the Q projection -- exact, 1/8 is a power of two)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, const size_t n,
                                  const float scale) {
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i] * scale);
 }

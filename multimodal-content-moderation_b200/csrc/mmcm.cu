@@ -402,7 +402,11 @@ struct mmcm_handle_s {
   cudaEvent_t ev_fork = nullptr, ev_text = nullptr, ev_vis = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
   // options
-  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 512, opt_debug_feats = 0, opt_auto_chunk = 1;
+  // CUDA graphs of whole forwards for small batches (launch-bound regime): key = (B, S, mask?, probs?)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int warm = 0; };
+  std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+  int opt_graph_max_batch = 0;   // off by default: small batches are bound by the GPU-side kernel chain, not the host
+  int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
 };
@@ -882,6 +886,26 @@ static int check_forward_args(Eng* e, const void* ids, const void* px, const voi
   return MMCM_OK;
 }
 
+static int ensure_static_io(Eng* e, int64_t B) {
+  const mmcm_config& c = e->cfg;
+  if (B <= e->host_cap) return MMCM_OK;
+  const int64_t px_per = (int64_t)3 * c.image * c.image;
+  CK(cudaDeviceSynchronize());
+  dfree(e, e->d_ids); dfree(e, e->d_mask); dfree(e, e->d_px); dfree(e, e->d_tp); dfree(e, e->d_ip);
+  dfree(e, e->d_logits); dfree(e, e->d_probs);
+  int64_t cap = e->host_cap ? e->host_cap : 64;
+  while (cap < B) cap *= 2;
+  CKR(dalloc(e, &e->d_ids, cap * c.max_pos)); CKR(dalloc(e, &e->d_mask, cap * c.max_pos));
+  CKR(dalloc(e, &e->d_px, cap * px_per));
+  CKR(dalloc(e, &e->d_tp, cap)); CKR(dalloc(e, &e->d_ip, cap));
+  CKR(dalloc(e, &e->d_logits, cap * c.num_outputs)); CKR(dalloc(e, &e->d_probs, cap * c.num_outputs));
+  e->host_cap = cap; e->host_S = c.max_pos;
+  // graphs captured earlier point into the freed buffers
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+  return MMCM_OK;
+}
+
 static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const float* px, const float* tp,
                           const float* ip, int B, int S, float* logits, float* probs, cudaStream_t st) {
   const mmcm_config& c = e->cfg;
@@ -981,6 +1005,7 @@ int mmcm_destroy(mmcm_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   clear_gemm_events(h->stats);
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   {  // cached tensor maps may point into freed memory that a later allocation re-uses with another shape
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1070,13 +1095,70 @@ int mmcm_finalize_weights(mmcm_handle h) {
   return MMCM_OK;
 }
 
+// Small batches are launch bound (~180 launches, 1.5 ms of host time for < 0.3 ms of GPU work): replay the whole
+// forward as one CUDA graph.  Inputs are copied into handle-owned buffers (graphs bake pointers), the first two calls
+// of a shape run eagerly (allocations, function attributes, TMA maps), the third is captured.
+static int forward_graphed(Eng* e, const int64_t* ids, const int64_t* mask, const float* px, const float* tp,
+                           const float* ip, int B, int S, float* logits, float* probs, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const mmcm_config& c = e->cfg;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return MMCM_OK;  // caller captures
+  auto key = std::make_tuple(B, S, mask ? 1 : 0, probs ? 1 : 0);
+  Eng::GraphEntry& g = e->graphs[key];
+  if (!g.exec && g.warm < 2) { g.warm++; return MMCM_OK; }   // eager warm-up calls
+  CKR(ensure_static_io(e, B));
+  Eng::GraphEntry& ge = e->graphs[key];                      // ensure_static_io may have cleared the map
+  const int64_t px_per = (int64_t)3 * c.image * c.image;
+  const int C = c.num_outputs;
+  CK(cudaMemcpyAsync(e->d_ids, ids, (size_t)B * S * 8, cudaMemcpyDeviceToDevice, st));
+  if (mask) CK(cudaMemcpyAsync(e->d_mask, mask, (size_t)B * S * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(e->d_px, px, (size_t)B * px_per * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(e->d_tp, tp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(e->d_ip, ip, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (!ge.exec) {
+    if (ge.warm >= 1000) return MMCM_OK;                     // capture failed before: stay eager for this shape
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int r = MMCM_OK;
+    if (ce == cudaSuccess) {
+      r = forward_device(e, e->d_ids, mask ? e->d_mask : nullptr, e->d_px, e->d_tp, e->d_ip, B, S, e->d_logits,
+                         probs ? e->d_probs : nullptr, st);
+      ce = cudaStreamEndCapture(st, &graph);
+    }
+    if (r == MMCM_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (r != MMCM_OK || ce != cudaSuccess || !ge.exec) {
+      cudaGetLastError();
+      ge.exec = nullptr;
+      ge.warm = 1000;
+      return MMCM_OK;                                        // eager path below handles this call
+    }
+    ge.launches = e->stats.launches;
+  }
+  CK(cudaGraphLaunch(ge.exec, st));
+  e->stats.launches = ge.launches;
+  e->last_B = B;
+  CK(cudaMemcpyAsync(logits, e->d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToDevice, st));
+  if (probs) CK(cudaMemcpyAsync(probs, e->d_probs, (size_t)B * C * 4, cudaMemcpyDeviceToDevice, st));
+  *handled = true;
+  return MMCM_OK;
+}
+
 int mmcm_forward(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask, const float* pixel_values,
                  const float* text_present, const float* image_present, int32_t B, int32_t S, float* logits_out,
                  float* probs_out, void* stream) {
   CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
   CK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B > 0 && B <= h->opt_graph_max_batch && !h->stats.time_gemms) {
+    bool handled = false;
+    CKR(forward_graphed(h, input_ids, attention_mask, pixel_values, text_present, image_present, B, S, logits_out,
+                        probs_out, st, &handled));
+    if (handled) return MMCM_OK;
+  }
   return forward_device(h, input_ids, attention_mask, pixel_values, text_present, image_present, B, S, logits_out,
-                        probs_out, reinterpret_cast<cudaStream_t>(stream));
+                        probs_out, st);
 }
 
 int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
@@ -1090,19 +1172,7 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   const mmcm_config& c = e->cfg;
   const int64_t px_per = (int64_t)3 * c.image * c.image;
   const int C = c.num_outputs;
-  if (B > e->host_cap || S > e->host_S) {
-    CK(cudaDeviceSynchronize());
-    dfree(e, e->d_ids); dfree(e, e->d_mask); dfree(e, e->d_px); dfree(e, e->d_tp); dfree(e, e->d_ip);
-    dfree(e, e->d_logits); dfree(e, e->d_probs);
-    int64_t cap = e->host_cap ? e->host_cap : 64;
-    while (cap < B) cap *= 2;
-    const int Sc = c.max_pos;
-    CKR(dalloc(e, &e->d_ids, cap * Sc)); CKR(dalloc(e, &e->d_mask, cap * Sc));
-    CKR(dalloc(e, &e->d_px, cap * px_per));
-    CKR(dalloc(e, &e->d_tp, cap)); CKR(dalloc(e, &e->d_ip, cap));
-    CKR(dalloc(e, &e->d_logits, cap * C)); CKR(dalloc(e, &e->d_probs, cap * C));
-    e->host_cap = cap; e->host_S = Sc;
-  }
+  CKR(ensure_static_io(e, B));
   // small inputs first, then the pixels in micro-batch chunks on the copy stream so that the H2D transfer of
   // chunk i+1 overlaps the towers of chunk i
   CK(cudaMemcpyAsync(e->d_ids, input_ids, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
@@ -1224,6 +1294,10 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "pdl") g_pdl = value != 0;   // process-wide: programmatic dependent launch on/off
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
+  else if (n == "graph_max_batch") {
+    if (value < 0 || value > 4096) return fail(MMCM_EINVAL, "graph_max_batch out of range");
+    h->opt_graph_max_batch = (int)value;
+  }
   else return fail(MMCM_EINVAL, "unknown option '%s'", name);
   return MMCM_OK;
 }

@@ -110,11 +110,14 @@ MMCM_API int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t
 /* Number of kernels this library launched during the last mmcm_forward on this handle. */
 MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
 /* CUDA-event time (ms) of the GEMM launches of the last forward when profiling was enabled with
- * mmcm_set_option(h, "time_gemms", 1); also returns their FLOPs. Synchronises the device. */
+ * mmcm_set_option(h, "time_gemms", 1); also returns the FLOPs they EXECUTED (2*M*N*K with the live row count of
+ * packed text chunks). Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 /* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel),
  * "micro_batch" (upper bound on the samples per internal pass of a tower), "auto_chunk" (1 = pick, per tower, the
  * chunk size <= micro_batch whose GEMM tile counts fill whole waves of the 148 SMs; 0 = use micro_batch as is),
+ * "varlen_text" (1 = default: the causal CLIP text tower keeps only the rows up to each sample's pooled EOS
+ * position, packed back to back -- bit-identical logits, fewer rows; 0 = compute all S rows like the reference),
  * "graph_max_batch" (forwards with B <= this are replayed as one CUDA graph from the third call of a shape on;
  * 0 = off = default: measured on B200 the 177-kernel chain of a B=1 forward is GPU-latency bound, 1.45 ms either way), "streams" (1 or 2: text/vision towers on separate streams), "pdl" (1 = launch every kernel with programmatic
  * stream serialization so that prologues overlap the previous kernel's tail; process-wide), "debug_feats" (0/1: keep the projected

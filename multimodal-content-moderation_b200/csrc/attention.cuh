@@ -36,7 +36,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // qkv  : bf16 [rows, 3*D]  (Q | K | V, Q already multiplied by dh^-1/2 -- folded into the weights)
 // out  : bf16 [rows, D]
 // seq_start/seq_len : per-sample first row and length (packed variable-length text) or nullptr => b*T, T
-// key_valid : uint8 [B, Tstride] (1 = key may be attended) or nullptr
+// key_valid : uint8 [B, Tstride] (1 = key may be attended; packed chunks: one byte per packed row) or nullptr
 // grid = (heads, B, ceil(TPAD/16/QW)), block = QW warps; warp w of query block z owns query rows
 // 16*(z*QW+w) .. +15.  Every CTA stages all keys/values of its (sample, head) but only its own query rows.
 template <int TPAD, int QW>
@@ -102,7 +102,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
   for (int t = tid; t < TPAD; t += nthr) {
     uint8_t ok = (t < T) ? 1 : 0;
-    if (ok && key_valid) ok = key_valid[(size_t)b * kv_stride + t] ? 1 : 0;
+    if (ok && key_valid) ok = key_valid[seq_start ? (size_t)(row0 + t) : (size_t)b * kv_stride + t] ? 1 : 0;
     kvs[t] = ok;
   }
   __syncthreads();

@@ -85,7 +85,7 @@ struct Gemm2Cfg {
 template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BLOCK_N>::THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const EpiParams ep, const int M, const int N, const int K) {
+                     const EpiParams ep, const int M_host, const int N, const int K) {
   using C = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES];    // used in the leader only
@@ -103,8 +103,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
 
   const int tiles_n = N / BLOCK_N;
-  const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = K / C::BLOCK_K;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
@@ -133,6 +131,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   // PDL: barrier init, TMEM allocation and the cluster handshake above overlapped the previous kernel's tail
   pdl_trigger();
   pdl_wait();
+  // packed variable-length text: the live row count is produced on the device by the previous kernel
+  const int M = ep.m_dev ? min(__ldg(ep.m_dev), M_host) : M_host;
+  const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

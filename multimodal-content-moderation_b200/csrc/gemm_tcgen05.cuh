@@ -36,6 +36,7 @@ struct EpiParams {
   int ldo;             // row pitch of out / resid in elements
   int P, T;            // EPI_PATCH_F32: patches per sample, tokens per sample (T-P leading class rows)
   int act;             // Act for EPI_BIAS_ACT_BF16
+  const int* m_dev;    // optional device-side row count (<= M): packed variable-length text chunks
   long long* trace;    // dev tool (mmcm_debug_set_gemm_trace): per-CTA clock64 stamps, 16 slots per CTA; else nullptr
 };
 
@@ -326,7 +327,7 @@ struct GemmCfg {
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const EpiParams ep, const int M, const int N, const int K, int* __restrict__ sched) {
+                    const EpiParams ep, const int M_host, const int N, const int K, int* __restrict__ sched) {
   using C = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES];
@@ -344,8 +345,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
 
   const int tiles_n = N / BLOCK_N;
-  const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = K / C::BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -376,6 +375,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // PDL: everything above overlapped the previous kernel's tail; its outputs (A, the residual) are safe to read now
   pdl_trigger();
   pdl_wait();
+  // packed variable-length text: the live row count is produced on the device by the previous kernel
+  const int M = ep.m_dev ? min(__ldg(ep.m_dev), M_host) : M_host;
+  const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
 
   if (warp == 0) {
     // ===================== tile scheduler + TMA producer =====================
@@ -542,11 +545,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 template <int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
                                                         const __nv_bfloat16* __restrict__ W, const EpiParams ep,
-                                                        const int M, const int N, const int K) {
+                                                        const int M_host, const int N, const int K) {
   __shared__ float As[32][33];
   __shared__ float Ws[32][33];
   pdl_trigger();
   pdl_wait();
+  const int M = ep.m_dev ? min(__ldg(ep.m_dev), M_host) : M_host;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};

@@ -176,8 +176,9 @@ static int get_sched(cudaStream_t st, int** out) {
 struct LaunchStats {
   int64_t launches = 0;
   bool time_gemms = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
-  double gemm_flops = 0;
+  struct GemmRec { cudaEvent_t e0, e1; double flops_per_row; int m_host; const int* m_dev; };
+  std::vector<GemmRec> gemm_events;      // per-GEMM CUDA events (time_gemms) + what is needed to count EXECUTED FLOPs
+  int text_chunk = 0;                    // packed text chunks of this forward (each owns one device row counter)
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM launcher
@@ -259,8 +260,7 @@ static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int ep
     stats->launches++;
     if (stats->time_gemms) {
       CK(cudaEventRecord(e1, st));
-      stats->gemm_events.emplace_back(e0, e1);
-      stats->gemm_flops += 2.0 * M * (double)N * K;
+      stats->gemm_events.push_back(LaunchStats::GemmRec{e0, e1, 2.0 * (double)N * K, M, ep.m_dev});
     }
   }
   return MMCM_OK;
@@ -268,12 +268,13 @@ static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int ep
 
 // ------------------------------------------------------------------------------------------------ other launchers
 static int launch_layernorm(const float* x, const float* g, const float* b, float eps, int rows, int D,
-                            const int* gather, bf16* out_bf16, float* out_f32, cudaStream_t st, LaunchStats* stats) {
+                            const int* gather, bf16* out_bf16, float* out_f32, cudaStream_t st, LaunchStats* stats,
+                            const int* rows_dev = nullptr) {
   if (rows <= 0) return MMCM_OK;
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
-  if (D == 512) CK(launch_k(layernorm_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
-  else if (D == 768) CK(launch_k(layernorm_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
-  else if (D == 1024) CK(launch_k(layernorm_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32));
+  if (D == 512) CK(launch_k(layernorm_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
+  else if (D == 768) CK(launch_k(layernorm_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
+  else if (D == 1024) CK(launch_k(layernorm_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
   else return fail(MMCM_EINVAL, "layernorm: unsupported width %d (512, 768, 1024)", D);
   CK(cudaGetLastError());
   if (stats) stats->launches++;
@@ -282,29 +283,30 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
 
 template <int TPAD, int QW>
 static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, int T, int heads, int causal,
-                      cudaStream_t st) {
+                      cudaStream_t st, const int* seq_start, const int* seq_len) {
   auto kern = attention_kernel<TPAD, QW>;
   constexpr int smem = attention_smem_bytes<TPAD, QW>();
   static AttrOnce once;
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int qblocks = (TPAD / 16 + QW - 1) / QW;
   dim3 grid(heads, B, qblocks);
-  CK(launch_k(kern, dim3(grid), dim3(QW * 32), smem, st, qkv, out, kvalid, nullptr, nullptr, T, heads * ATT_DH, causal, T));
+  CK(launch_k(kern, dim3(grid), dim3(QW * 32), smem, st, qkv, out, kvalid, seq_start, seq_len, T, heads * ATT_DH, causal, T));
   CK(cudaGetLastError());
   return MMCM_OK;
 }
 
 static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
-                            cudaStream_t st, LaunchStats* stats) {
+                            cudaStream_t st, LaunchStats* stats, const int* seq_start = nullptr,
+                            const int* seq_len = nullptr) {
   if (B <= 0) return MMCM_OK;
   int r;
-  if (T <= 16) r = launch_att<16, 1>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 32) r = launch_att<32, 2>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 64) r = launch_att<64, 4>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 80) r = launch_att<80, 5>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 128) r = launch_att<128, 8>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 208) r = launch_att<208, 7>(qkv, out, kvalid, B, T, heads, causal, st);
-  else if (T <= 256) r = launch_att<256, 8>(qkv, out, kvalid, B, T, heads, causal, st);
+  if (T <= 16) r = launch_att<16, 1>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 32) r = launch_att<32, 2>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 64) r = launch_att<64, 4>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 80) r = launch_att<80, 5>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 128) r = launch_att<128, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 208) r = launch_att<208, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 256) r = launch_att<256, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else return fail(MMCM_EINVAL, "attention: sequence length %d > 256 is not supported", T);
   CKR(r);
   if (stats) stats->launches++;
@@ -356,6 +358,7 @@ struct Arena {  // activations of one tower for one micro-batch
   bf16* att = nullptr;   // [rows, D]
   bf16* ff = nullptr;    // [rows, F]
   int* pool_row = nullptr;
+  int *seq_start = nullptr, *seq_len = nullptr, *rows_dev = nullptr;   // packed variable-length text
   int64_t rows = 0;
 };
 
@@ -406,6 +409,7 @@ struct mmcm_handle_s {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int warm = 0; };
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
   int opt_graph_max_batch = 0;   // off by default: small batches are bound by the GPU-side kernel chain, not the host
+  int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
@@ -641,6 +645,7 @@ static int setup_weights(Eng* e) {
 // ------------------------------------------------------------------------------------------------ arenas
 static void free_arena(Eng* e, Arena& a) {
   dfree(e, a.x); dfree(e, a.h); dfree(e, a.qkv); dfree(e, a.att); dfree(e, a.ff); dfree(e, a.pool_row);
+  dfree(e, a.seq_start); dfree(e, a.seq_len); dfree(e, a.rows_dev);
   a = Arena();
 }
 static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) {
@@ -651,6 +656,9 @@ static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) 
   CKR(dalloc(e, &a.att, rows * t.D));
   CKR(dalloc(e, &a.ff, rows * t.F));
   CKR(dalloc(e, &a.pool_row, mb));
+  CKR(dalloc(e, &a.seq_start, mb));
+  CKR(dalloc(e, &a.seq_len, mb));
+  CKR(dalloc(e, &a.rows_dev, 256));   // one live-row counter per packed chunk of a forward (accounting reads them back)
   return MMCM_OK;
 }
 
@@ -741,30 +749,34 @@ static int ensure_batch(Eng* e, int64_t B) {
 
 // ------------------------------------------------------------------------------------------------ towers
 static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T, const uint8_t* kvalid, int causal,
-                      cudaStream_t st) {
+                      cudaStream_t st, const int* packed_rows = nullptr) {
   LaunchStats* S = &e->stats;
   const int D = t.D, F = t.F, impl = e->opt_gemm_impl;
+  const bool packed = packed_rows != nullptr;
+  const int* rdev = packed_rows;                             // live row count of a packed chunk (device side)
+  const int* sstart = packed ? a.seq_start : nullptr;
+  const int* slen = packed ? a.seq_len : nullptr;
   for (int i = 0; i < t.L; ++i) {
     const LayerW& w = t.layers[i];
     // h = LN1(x)                                               HF clip :372
-    CKR(launch_layernorm(a.x, w.ln1g, w.ln1b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    CKR(launch_layernorm(a.x, w.ln1g, w.ln1b, t.eps, rows, D, nullptr, a.h, nullptr, st, S, rdev));
     // qkv = h @ [Wq*s | Wk | Wv]^T + [bq*s | bk | bv]          HF clip :313-319
     EpiParams ep{};
-    ep.bias = w.bqkv; ep.out = a.qkv; ep.ldo = 3 * D;
+    ep.bias = w.bqkv; ep.out = a.qkv; ep.ldo = 3 * D; ep.m_dev = rdev;
     CKR(launch_gemm(a.h, w.wqkv, rows, 3 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
     // att = softmax(q k^T + mask) v                            HF clip :321-332
-    CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S));
+    CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S, sstart, slen));
     // x = x + att @ Wo^T + bo                                  HF clip :334, :379
     ep = EpiParams{};
-    ep.bias = w.bo; ep.out = a.x; ep.resid = a.x; ep.ldo = D;
+    ep.bias = w.bo; ep.out = a.x; ep.resid = a.x; ep.ldo = D; ep.m_dev = rdev;
     CKR(launch_gemm(a.att, w.wo, rows, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
     // h = LN2(x); ff = act(h @ W1^T + b1); x = x + ff @ W2^T + b2      HF clip :381-384, :347-351
-    CKR(launch_layernorm(a.x, w.ln2g, w.ln2b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    CKR(launch_layernorm(a.x, w.ln2g, w.ln2b, t.eps, rows, D, nullptr, a.h, nullptr, st, S, rdev));
     ep = EpiParams{};
-    ep.bias = w.b1; ep.out = a.ff; ep.ldo = F; ep.act = t.act;
+    ep.bias = w.b1; ep.out = a.ff; ep.ldo = F; ep.act = t.act; ep.m_dev = rdev;
     CKR(launch_gemm(a.h, w.w1, rows, F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
     ep = EpiParams{};
-    ep.bias = w.b2; ep.out = a.x; ep.resid = a.x; ep.ldo = D;
+    ep.bias = w.b2; ep.out = a.x; ep.resid = a.x; ep.ldo = D; ep.m_dev = rdev;
     CKR(launch_gemm(a.ff, w.w2, rows, D, F, EPI_BIAS_RESID_F32, ep, impl, st, S));
   }
   return MMCM_OK;
@@ -778,16 +790,29 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
   const bool clip = c.backend == MMCM_BACKEND_CLIP;
   const int blocks = (rows + 7) / 8;
   const int eos = clip ? c.eos_id : -1;
-  if (t.D == 512)
-    CK(launch_k(text_embed_kernel<512>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
-                                                   a.pool_row, e->key_valid));
-  else if (t.D == 768)
-    CK(launch_k(text_embed_kernel<768>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
-                                                   a.pool_row, e->key_valid));
-  else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
-  CK(cudaGetLastError());
-  e->stats.launches++;
-  CKR(run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st));
+  const bool packed = clip && e->opt_varlen_text;   // exact for the causal CLIP tower only (see text_plan_kernel)
+  int* const rows_slot = a.rows_dev + (e->stats.text_chunk++ & 255);
+  if (packed) {
+    CK(launch_k(text_plan_kernel, dim3(1), dim3(1024), 0, st, ids, n, S, eos, a.seq_start, a.seq_len, a.pool_row, rows_slot));
+    if (t.D == 512)
+      CK(launch_k(text_embed_packed_kernel<512>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S,
+                  c.vocab, a.seq_start, a.seq_len, a.x, e->key_valid));
+    else if (t.D == 768)
+      CK(launch_k(text_embed_packed_kernel<768>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S,
+                  c.vocab, a.seq_start, a.seq_len, a.x, e->key_valid));
+    else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
+    e->stats.launches += 2;
+  } else {
+    if (t.D == 512)
+      CK(launch_k(text_embed_kernel<512>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                  a.pool_row, e->key_valid));
+    else if (t.D == 768)
+      CK(launch_k(text_embed_kernel<768>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S, c.vocab, eos, a.x,
+                  a.pool_row, e->key_valid));
+    else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
+    e->stats.launches++;
+  }
+  CKR(run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr));
   // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
   CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
   e->last_text_rows = rows;
@@ -866,11 +891,11 @@ static int run_head(Eng* e, const float* tp, const float* ip, int B, float* logi
 
 static void clear_gemm_events(LaunchStats& s) {
   for (auto& p : s.gemm_events) {
-    cudaEventDestroy(p.first);
-    cudaEventDestroy(p.second);
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
   }
   s.gemm_events.clear();
-  s.gemm_flops = 0;
+  s.text_chunk = 0;
 }
 
 static int check_forward_args(Eng* e, const void* ids, const void* px, const void* tp, const void* ip, int B, int S,
@@ -1265,14 +1290,20 @@ int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* la
   if (!h) return fail(MMCM_EINVAL, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  double ms = 0;
+  double ms = 0, flops = 0;
   for (auto& p : h->stats.gemm_events) {
     float t = 0;
-    CK(cudaEventElapsedTime(&t, p.first, p.second));
+    CK(cudaEventElapsedTime(&t, p.e0, p.e1));
     ms += t;
+    int m = p.m_host;
+    if (p.m_dev) {   // packed text chunk: count the rows that were actually multiplied
+      CK(cudaMemcpy(&m, p.m_dev, sizeof(int), cudaMemcpyDeviceToHost));
+      if (m > p.m_host) m = p.m_host;
+    }
+    flops += p.flops_per_row * m;
   }
   if (ms_out) *ms_out = ms;
-  if (flops_out) *flops_out = h->stats.gemm_flops;
+  if (flops_out) *flops_out = flops;
   if (launches_out) *launches_out = (int64_t)h->stats.gemm_events.size();
   return MMCM_OK;
 }
@@ -1294,6 +1325,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "pdl") g_pdl = value != 0;   // process-wide: programmatic dependent launch on/off
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
+  else if (n == "varlen_text") h->opt_varlen_text = value != 0;
   else if (n == "graph_max_batch") {
     if (value < 0 || value > 4096) return fail(MMCM_EINVAL, "graph_max_batch out of range");
     h->opt_graph_max_batch = (int)value;

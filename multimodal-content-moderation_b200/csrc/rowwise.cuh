@@ -18,11 +18,12 @@ namespace mmcm {
 template <int D>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 const float eps, const int rows, const int* __restrict__ gather,
-                 __nv_bfloat16* __restrict__ out_bf16, float* out_f32) {
+                 const float eps, const int rows_host, const int* __restrict__ gather,
+                 __nv_bfloat16* __restrict__ out_bf16, float* out_f32, const int* __restrict__ rows_dev) {
   constexpr int V = D / 128;  // float4 per lane
   pdl_trigger();
   pdl_wait();
+  const int rows = rows_dev ? min(__ldg(rows_dev), rows_host) : rows_host;   // packed text: live rows known on device
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -128,6 +129,98 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
     }
     if (lane == 0) pool_row[b] = b * S + best;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5' packed (variable-length) CLIP text chunks.  The CLIP text tower is causal and only the EOS row is pooled
+// (HF clip :546-551, :575-584), so rows after the pooled position never influence the consumed row: measured on the
+// reference, truncating at EOS changes the pooled output by 2.4e-6 = fp32 rounding.  text_plan_kernel
+// computes, per sample, the pooled index p_b (same rules as text_embed_kernel), keeps L_b = p_b + 1 rows and
+// prefix-sums them; text_embed_packed_kernel writes only those rows, back to back.  One block, B <= 4096.
+//   seq_start[b], seq_len[b]        packed coordinates of sample b
+//   pool_row[b] = seq_start[b] + p_b
+//   rows_total[0] = sum_b L_b        (device-side M of every GEMM / LayerNorm of the chunk)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+text_plan_kernel(const int64_t* __restrict__ ids, const int B, const int S, const int eos_id,
+                 int* __restrict__ seq_start, int* __restrict__ seq_len, int* __restrict__ pool_row,
+                 int* __restrict__ rows_total) {
+  __shared__ int warp_tot[32], warp_excl[32];
+  __shared__ int carry, slab_total;
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int b = base + tid;
+    int len = 0;
+    if (b < B) {
+      const int64_t* row = ids + (size_t)b * S;
+      int best = 0;
+      if (eos_id == 2) {            // legacy branch: argmax(ids), first maximum (HF clip :564-574)
+        int bv = (int)row[0];
+        for (int t = 1; t < S; ++t) { const int v = (int)row[t]; if (v > bv) { bv = v; best = t; } }
+      } else {                      // first position equal to eos, 0 if none (HF clip :575-584)
+        for (int t = 0; t < S; ++t) if ((int)row[t] == eos_id) { best = t; break; }
+      }
+      len = best + 1;
+    }
+    int incl = len;                 // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {                // scan of the 32 warp totals
+      const int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+      warp_excl[lane] = wi - w;
+      if (lane == 31) slab_total = wi;
+    }
+    __syncthreads();
+    const int excl = carry + warp_excl[warp] + incl - len;
+    if (b < B) {
+      seq_start[b] = excl;
+      seq_len[b] = len;
+      pool_row[b] = excl + len - 1;
+    }
+    __syncthreads();
+    if (tid == 0) carry += slab_total;
+    __syncthreads();
+  }
+  if (tid == 0) rows_total[0] = carry;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+text_embed_packed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                         const float* __restrict__ tok, const float* __restrict__ pos, const int B, const int S,
+                         const int vocab, const int* __restrict__ seq_start, const int* __restrict__ seq_len,
+                         float* __restrict__ x, uint8_t* __restrict__ key_valid) {
+  constexpr int V = D / 128;
+  pdl_trigger();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * S) return;
+  const int b = warp / S, s = warp - b * S;
+  if (s >= seq_len[b]) return;
+  const int orow = seq_start[b] + s;
+  long long id = ids[warp];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;
+  const float4* tr = reinterpret_cast<const float4*>(tok + (size_t)id * D);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (size_t)s * D);
+  float4* xo = reinterpret_cast<float4*>(x + (size_t)orow * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 a = __ldg(tr + lane + 32 * i), p = __ldg(pr + lane + 32 * i);
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    xo[lane + 32 * i] = a;
+  }
+  if (lane == 0) key_valid[orow] = mask ? (mask[warp] != 0 ? 1 : 0) : 1;
 }
 
 // ------------------------------------------------------------------------------------------------

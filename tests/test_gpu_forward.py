@@ -194,3 +194,36 @@ def test_cuda_graph_replay_matches_eager():
     assert torch.equal(m.predict_proba(**b1), torch.sigmoid(e1)) or \
         torch.allclose(m.predict_proba(**b1), torch.sigmoid(e1), atol=1e-6)
     assert m._engine.last_launch_count() > 100
+
+
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened"])
+def test_packed_varlen_text_is_bit_identical_to_dense(name):
+    """varlen_text packs the causal CLIP text tower up to each sample's pooled row: same per-row arithmetic, so the
+    logits must be IDENTICAL to the dense path (all S rows), including the edge rows (no EOS -> 1 row, EOS at 1, full)."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    for B, seed in ((8, 31), (77, 32), (300, 33)):
+        batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, B, seed=seed, edge_rows=True).items()}
+        m.set_option("varlen_text", 0)
+        dense = m(**batch)["logits"].clone()
+        tp_dense = m._engine.stage("text_pooled").clone()
+        m.set_option("varlen_text", 1)
+        packed = m(**batch)["logits"]
+        assert torch.equal(m._engine.stage("text_pooled"), tp_dense)
+        assert torch.equal(packed, dense)
+    # legacy eos_token_id == 2 checkpoints pool at argmax(ids): rebuild the engine with that rule
+    import mmcm_b200 as P
+    from dataclasses import replace
+    legacy = replace(a, eos_id=2)
+    eng = P.Engine(legacy, m._head, 5, 512, m._head_hidden_dim, 0)
+    eng.load_state_dict(sd)
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 16, seed=34, edge_rows=True).items()}
+    eng.set_option("varlen_text", 0)
+    d = eng.forward(batch["input_ids"], batch["attention_mask"], batch["pixel_values"], batch["text_present"],
+                    batch["image_present"]).clone()
+    eng.set_option("varlen_text", 1)
+    p_ = eng.forward(batch["input_ids"], batch["attention_mask"], batch["pixel_values"], batch["text_present"],
+                     batch["image_present"])
+    assert torch.equal(p_, d)
+    eng.close()

@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--varlen", type=int, default=0,
                     help="1 = packed variable-length CLIP text (exact, fewer rows); the headline keeps 0 = every "
                          "one of the S rows the reference computes, the packed number is reported under `extras`")
+    ap.add_argument("--pairs-text", type=int, default=0, help="CTA pairs the text-tower GEMMs may occupy (0 = all 74)")
+    ap.add_argument("--pairs-vision", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -207,6 +209,8 @@ def main():
     m.set_option("streams", args.streams)
     m.set_option("pdl", args.pdl)
     m.set_option("varlen_text", args.varlen)
+    m.set_option("pairs_text", args.pairs_text)
+    m.set_option("pairs_vision", args.pairs_vision)
     eng = m._ensure_engine(local_rank)
 
     B = args.batch

@@ -146,6 +146,18 @@ MMCM_API int mmcm_layernorm(const float* x, const float* gamma, const float* bet
  * key_valid uint8 [B,T] or NULL; causal 0/1; out bf16 [B*T, D]. A query with no admissible key yields 0. */
 MMCM_API int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B, int32_t T, int32_t heads,
                    int32_t causal, void* out, void* stream);
+/* --- the callers' pre- and post-processing, device pointers ----------------------------------------
+ * ToTensor + Normalize of the eval transform (R/src/data/dataset.py:106-111) for an already resized/cropped uint8
+ * HWC image batch [B,H,W,3]: chw_out[b,c,y,x] = (u8/255 - mean[c]) / std[c], fp32 [B,3,H,W], bit-identical to
+ * torchvision.  mean3 / std3 are HOST pointers to 3 floats. W % 4 == 0. */
+MMCM_API int mmcm_preprocess_u8(const uint8_t* hwc, int32_t B, int32_t H, int32_t W, const float* mean3,
+                                const float* std3, float* chw_out, void* stream);
+/* probs = 1/(1+exp(-logits)); decisions[b,c] = probs >= thresholds[c]; any[b] = OR_c decisions
+ * (R/scripts/inference.py:218-232); when labels != NULL, confusion_accum[c*4 + {0,1,2,3}] += {TP,FP,FN,TN}
+ * (the counts behind f1/precision/recall of R/src/training/metrics.py:180-205).  Outputs may be NULL. C <= 64. */
+MMCM_API int mmcm_postprocess(const float* logits, const float* thresholds, const float* labels, int32_t B, int32_t C,
+                              float* probs_out, uint8_t* decisions_out, uint8_t* any_out, uint64_t* confusion_accum,
+                              void* stream);
 /* Dev tool: when device_buffer != NULL, mmcm_gemm_bf16 (impl 0) writes 16 clock64 stamps per CTA into it
  * (>= 148 * 16 int64); NULL switches tracing off. */
 MMCM_API int mmcm_debug_set_gemm_trace(void* device_buffer);

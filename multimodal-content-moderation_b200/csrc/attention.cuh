@@ -37,179 +37,225 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // out  : bf16 [rows, D]
 // seq_start/seq_len : per-sample first row and length (packed variable-length text) or nullptr => b*T, T
 // key_valid : uint8 [B, Tstride] (1 = key may be attended; packed chunks: one byte per packed row) or nullptr
-// grid = (heads, B, ceil(TPAD/16/QW)), block = QW warps; warp w of query block z owns query rows
-// 16*(z*QW+w) .. +15.  Every CTA stages all keys/values of its (sample, head) but only its own query rows.
+//
+// Persistent and software-pipelined: a CTA (QW warps) walks work items (sample b, head h, query block z) with stride
+// gridDim.x; while it computes item i out of one shared-memory buffer, cp.async (LDGSTS, 16 B, zero-fill for padding
+// rows) is already filling the other buffer with item i+1.  The first version staged, synchronised, computed and
+// stored one item per CTA and reached 47 % of the HBM roofline (profiles/r01_attention_layernorm_ncu_full.txt):
+// latency bound, nothing in flight during the math.  Warp w of query block z owns query rows 16*(z*QW+w) .. +15.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TPAD, int QW>
+struct AttCfg {
+  static constexpr int QROWS = QW * 16;
+  static constexpr int BUF_BYTES = ((2 * TPAD + QROWS) * ATT_LD * 2 + TPAD + 15) / 16 * 16;
+  static constexpr int SMEM_BYTES = 2 * BUF_BYTES;
+  static constexpr int QBLOCKS = (TPAD / 16 + QW - 1) / QW;
+};
+
 template <int TPAD, int QW>
 __global__ void __launch_bounds__(QW * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const uint8_t* __restrict__ key_valid, const int* __restrict__ seq_start,
                  const int* __restrict__ seq_len, const int T_fixed, const int D, const int causal,
-                 const int kv_stride) {
+                 const int kv_stride, const int B, const int heads) {
   static_assert(TPAD % 16 == 0, "TPAD must be a multiple of 16");
+  using C = AttCfg<TPAD, QW>;
   constexpr int NT = TPAD / 8;   // key tiles of 8
   constexpr int KT = TPAD / 16;  // key steps of 16 for P V
+  constexpr int NTHR = QW * 32;
   extern __shared__ __align__(16) uint8_t att_smem[];
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(att_smem);   // [QW*16][ATT_LD], local query rows
-  __nv_bfloat16* Ks = Qs + QW * 16 * ATT_LD;
-  __nv_bfloat16* Vs = Ks + TPAD * ATT_LD;
-  uint8_t* kvs = reinterpret_cast<uint8_t*>(Vs + TPAD * ATT_LD);
 
   pdl_trigger();
   pdl_wait();
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int T = seq_len ? seq_len[b] : T_fixed;
-  const int row0 = seq_start ? seq_start[b] : b * T_fixed;
-  const int ld_qkv = 3 * D;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int q0 = blockIdx.z * QW * 16;   // first query row of this CTA
-  if (q0 >= T) return;                   // whole CTA is padding (uniform exit before any barrier)
-
-  // ---- stage K, V (all keys) and Q (own rows) of this (sample, head): 8 x 16-byte chunks per row; zero the padding.
-  // All global loads of a thread are issued before its first shared-memory store (fully unrolled, independent),
-  // so a CTA has its whole working set in flight at once instead of one 16-byte load per thread at a time.
-  {
-    constexpr int NTHR = QW * 32;
-    constexpr int KV_CHUNKS = TPAD * 16;
-    constexpr int KV_ITERS = (KV_CHUNKS + NTHR - 1) / NTHR;
-    uint4 kv[KV_ITERS], qv[4];
-#pragma unroll
-    for (int i = 0; i < KV_ITERS; ++i) {
-      const int idx = tid + i * NTHR;
-      const int t = idx >> 4, c = idx & 15;
-      kv[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (idx < KV_CHUNKS && t < T)
-        kv[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + t) * ld_qkv + (1 + (c >> 3)) * D + h * ATT_DH +
-                                                     (c & 7) * 8));
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {   // QW*16 rows x 8 chunks = 4 per thread
-      const int idx = tid + i * NTHR;
-      const int t = q0 + (idx >> 3);
-      qv[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (t < T) qv[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + t) * ld_qkv + h * ATT_DH + (idx & 7) * 8));
-    }
-#pragma unroll
-    for (int i = 0; i < KV_ITERS; ++i) {
-      const int idx = tid + i * NTHR;
-      const int t = idx >> 4, c = idx & 15;
-      if (idx < KV_CHUNKS) *reinterpret_cast<uint4*>(((c >> 3) == 0 ? Ks : Vs) + t * ATT_LD + (c & 7) * 8) = kv[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * NTHR;
-      *reinterpret_cast<uint4*>(Qs + (idx >> 3) * ATT_LD + (idx & 7) * 8) = qv[i];
-    }
-  }
-  for (int t = tid; t < TPAD; t += nthr) {
-    uint8_t ok = (t < T) ? 1 : 0;
-    if (ok && key_valid) ok = key_valid[seq_start ? (size_t)(row0 + t) : (size_t)b * kv_stride + t] ? 1 : 0;
-    kvs[t] = ok;
-  }
-  __syncthreads();
-
+  const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
-  const int r0 = q0 + warp * 16;
-  if (r0 >= T) return;  // whole warp is padding (no further block-wide barriers below)
+  const int ld_qkv = 3 * D;
+  const int total = B * heads * C::QBLOCKS;
 
-  // ---- S = Q K^T
-  uint32_t qa[4][4];
-  {
-    const int m = lane >> 3, rr = lane & 7;
-    const int qrow = warp * 16 + rr + ((m & 1) ? 8 : 0);  // local row inside Qs
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int col = kk * 16 + ((m & 2) ? 8 : 0);
-      ldmatrix_x4(qa[kk], smem_u32(Qs + qrow * ATT_LD + col));
+  // item -> (b, h, z): h fastest so that neighbouring CTAs read neighbouring 128-byte column blocks of the same rows
+  auto decode = [&](int item, int& b, int& h, int& z) {
+    h = item % heads;
+    const int r = item / heads;
+    z = r % C::QBLOCKS;
+    b = r / C::QBLOCKS;
+  };
+  // issue the asynchronous copies of one item into buffer `buf` (every thread, no barrier)
+  auto prefetch = [&](int item, int buf) {
+    int b, h, z;
+    decode(item, b, h, z);
+    const int T = seq_len ? seq_len[b] : T_fixed;
+    const int row0 = seq_start ? seq_start[b] : b * T_fixed;
+    const int q0 = z * C::QROWS;
+    uint8_t* base = att_smem + buf * C::BUF_BYTES;
+    const uint32_t Qs = smem_u32(base);
+    const uint32_t Ks = Qs + C::QROWS * ATT_LD * 2;
+    const uint32_t Vs = Ks + TPAD * ATT_LD * 2;
+    uint8_t* kvs = base + (2 * TPAD + C::QROWS) * ATT_LD * 2;
+    if (q0 < T) {   // (a query block that is pure padding loads nothing and is skipped by compute)
+      for (int idx = tid; idx < TPAD * 16; idx += NTHR) {
+        const int t = idx >> 4, c = idx & 15;
+        const bool in = t < T;
+        const __nv_bfloat16* src = qkv + (size_t)(row0 + (in ? t : 0)) * ld_qkv + (1 + (c >> 3)) * D + h * ATT_DH + (c & 7) * 8;
+        cp_async16(((c >> 3) == 0 ? Ks : Vs) + (t * ATT_LD + (c & 7) * 8) * 2, src, in ? 16u : 0u);
+      }
+      for (int idx = tid; idx < C::QROWS * 8; idx += NTHR) {
+        const int tl = idx >> 3, t = q0 + tl;
+        const bool in = t < T;
+        const __nv_bfloat16* src = qkv + (size_t)(row0 + (in ? t : 0)) * ld_qkv + h * ATT_DH + (idx & 7) * 8;
+        cp_async16(Qs + (tl * ATT_LD + (idx & 7) * 8) * 2, src, in ? 16u : 0u);
+      }
+      for (int t = tid; t < TPAD; t += NTHR) {
+        uint8_t ok = (t < T) ? 1 : 0;
+        if (ok && key_valid) ok = key_valid[seq_start ? (size_t)(row0 + t) : (size_t)b * kv_stride + t] ? 1 : 0;
+        kvs[t] = ok;
+      }
     }
-  }
-  float s[NT][4];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    const int m = lane >> 3, rr = lane & 7;
-    const int krow = j * 8 + rr;
-    uint32_t kb0[4], kb1[4];
-    ldmatrix_x4(kb0, smem_u32(Ks + krow * ATT_LD + m * 8));        // dh 0..31 : (b0,b1) of k-steps 0,1
-    ldmatrix_x4(kb1, smem_u32(Ks + krow * ATT_LD + 32 + m * 8));   // dh 32..63: (b0,b1) of k-steps 2,3
-    mma_bf16_16816(s[j], qa[0], kb0[0], kb0[1]);
-    mma_bf16_16816(s[j], qa[1], kb0[2], kb0[3]);
-    mma_bf16_16816(s[j], qa[2], kb1[0], kb1[1]);
-    mma_bf16_16816(s[j], qa[3], kb1[2], kb1[3]);
-  }
+  };
 
-  // ---- mask + fp32 softmax (rows g and g+8 of this warp's 16-row slab live in one quad)
-  const int qr0 = r0 + g, qr1 = r0 + g + 8;
-  float mx0 = -INFINITY, mx1 = -INFINITY;
+  int item = blockIdx.x;
+  int buf = 0;
+  if (item < total) prefetch(item, 0);
+  cp_async_commit();
+  for (; item < total; item += gridDim.x) {
+    const int next = item + gridDim.x;
+    if (next < total) prefetch(next, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();          // everything but the newest group (= the next item) has landed
+    __syncthreads();
+
+    int b, h, z;
+    decode(item, b, h, z);
+    const int T = seq_len ? seq_len[b] : T_fixed;
+    const int row0 = seq_start ? seq_start[b] : b * T_fixed;
+    const int q0 = z * C::QROWS;
+    const int r0 = q0 + warp * 16;
+    if (r0 < T) {                // warp-uniform: warps whose 16 rows are padding skip the math, not the barriers
+      uint8_t* base = att_smem + buf * C::BUF_BYTES;
+      const __nv_bfloat16* Qs = reinterpret_cast<const __nv_bfloat16*>(base);
+      const __nv_bfloat16* Ks = Qs + C::QROWS * ATT_LD;
+      const __nv_bfloat16* Vs = Ks + TPAD * ATT_LD;
+      const uint8_t* kvs = base + (2 * TPAD + C::QROWS) * ATT_LD * 2;
+
+      // ---- S = Q K^T
+      uint32_t qa[4][4];
+      {
+        const int m = lane >> 3, rr = lane & 7;
+        const int qrow = warp * 16 + rr + ((m & 1) ? 8 : 0);  // local row inside Qs
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int col = kk * 16 + ((m & 2) ? 8 : 0);
+          ldmatrix_x4(qa[kk], smem_u32(Qs + qrow * ATT_LD + col));
+        }
+      }
+      float s[NT][4];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int key = j * 8 + 2 * tq + e;
-      const bool kok = kvs[key] != 0;
-      const bool ok0 = kok && (!causal || key <= qr0);
-      const bool ok1 = kok && (!causal || key <= qr1);
-      s[j][e] = ok0 ? s[j][e] : -INFINITY;
-      s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
-      mx0 = fmaxf(mx0, s[j][e]);
-      mx1 = fmaxf(mx1, s[j][2 + e]);
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const int m = lane >> 3, rr = lane & 7;
+        const int krow = j * 8 + rr;
+        uint32_t kb0[4], kb1[4];
+        ldmatrix_x4(kb0, smem_u32(Ks + krow * ATT_LD + m * 8));        // dh 0..31 : (b0,b1) of k-steps 0,1
+        ldmatrix_x4(kb1, smem_u32(Ks + krow * ATT_LD + 32 + m * 8));   // dh 32..63: (b0,b1) of k-steps 2,3
+        mma_bf16_16816(s[j], qa[0], kb0[0], kb0[1]);
+        mma_bf16_16816(s[j], qa[1], kb0[2], kb0[3]);
+        mma_bf16_16816(s[j], qa[2], kb1[0], kb1[1]);
+        mma_bf16_16816(s[j], qa[3], kb1[2], kb1[3]);
+      }
+
+      // ---- mask + fp32 softmax (rows g and g+8 of this warp's 16-row slab live in one quad)
+      // key validity as bit masks (one 32-bit word per 32 keys, built once per item from the staged bytes) instead
+      // of a shared-memory byte load + compare per score: the kernel is instruction-issue bound (profiles/), so the
+      // per-element work is kept to: select, max | FFMA, EX2, add.
+      const int qr0 = r0 + g, qr1 = r0 + g + 8;
+      uint32_t vmask[(TPAD + 31) / 32];
+#pragma unroll
+      for (int w = 0; w < (TPAD + 31) / 32; ++w) {
+        const int key = w * 32 + lane;
+        vmask[w] = __ballot_sync(0xffffffffu, key < TPAD && kvs[key] != 0);
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = j * 8 + 2 * tq + e;
+          const bool kok = (vmask[(j * 8) / 32] >> (key & 31)) & 1u;
+          const bool ok0 = kok && (!causal || key <= qr0);
+          const bool ok1 = kok && (!causal || key <= qr1);
+          s[j][e] = ok0 ? s[j][e] : -INFINITY;
+          s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
+          mx0 = fmaxf(mx0, s[j][e]);
+          mx1 = fmaxf(mx1, s[j][2 + e]);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      if (mx0 == -INFINITY) mx0 = 0.f;  // fully masked row: exp(-inf) = 0 everywhere, sum = 0 -> output 0
+      if (mx1 == -INFINITY) mx1 = 0.f;
+      const float L2E = 1.4426950408889634f;
+      const float nm0 = -mx0 * L2E, nm1 = -mx1 * L2E;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = exp2f(fmaf(s[j][0], L2E, nm0));
+        s[j][1] = exp2f(fmaf(s[j][1], L2E, nm0));
+        s[j][2] = exp2f(fmaf(s[j][2], L2E, nm1));
+        s[j][3] = exp2f(fmaf(s[j][3], L2E, nm1));
+        sum0 += s[j][0] + s[j][1];
+        sum1 += s[j][2] + s[j][3];
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f;
+      const float inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+
+      // ---- O = P V   (P: accumulator layout of two adjacent key tiles == A fragment of one 16-key step)
+      float o[8][4];
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd) o[jd][0] = o[jd][1] = o[jd][2] = o[jd][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int m = lane >> 3, rr = lane & 7;
+        const int vrow = kk * 16 + rr + ((m & 1) ? 8 : 0);
+#pragma unroll
+        for (int jd = 0; jd < 8; jd += 2) {
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, smem_u32(Vs + vrow * ATT_LD + (jd + (m >> 1)) * 8));
+          mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
+        }
+      }
+
+      // ---- normalise and store (bf16x2 per thread per 8-wide dh tile)
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd) {
+        const int col = h * ATT_DH + jd * 8 + 2 * tq;
+        if (qr0 < T)
+          *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + qr0) * D + col) = pack_bf16x2(o[jd][0] * inv0, o[jd][1] * inv0);
+        if (qr1 < T)
+          *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + qr1) * D + col) = pack_bf16x2(o[jd][2] * inv1, o[jd][3] * inv1);
+      }
     }
+    __syncthreads();             // everyone is done with `buf` before the prefetch of the iteration after next refills it
+    buf ^= 1;
   }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  if (mx0 == -INFINITY) mx0 = 0.f;  // fully masked row: exp(-inf) = 0 everywhere, sum = 0 -> output 0
-  if (mx1 == -INFINITY) mx1 = 0.f;
-  const float L2E = 1.4426950408889634f;
-  float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    s[j][0] = exp2f((s[j][0] - mx0) * L2E);
-    s[j][1] = exp2f((s[j][1] - mx0) * L2E);
-    s[j][2] = exp2f((s[j][2] - mx1) * L2E);
-    s[j][3] = exp2f((s[j][3] - mx1) * L2E);
-    sum0 += s[j][0] + s[j][1];
-    sum1 += s[j][2] + s[j][3];
-  }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-  const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f;
-  const float inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-
-  // ---- O = P V   (P: accumulator layout of two adjacent key tiles == A fragment of one 16-key step)
-  float o[8][4];
-#pragma unroll
-  for (int jd = 0; jd < 8; ++jd) o[jd][0] = o[jd][1] = o[jd][2] = o[jd][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < KT; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-    const int m = lane >> 3, rr = lane & 7;
-    const int vrow = kk * 16 + rr + ((m & 1) ? 8 : 0);
-#pragma unroll
-    for (int jd = 0; jd < 8; jd += 2) {
-      uint32_t vb[4];
-      ldmatrix_x4_trans(vb, smem_u32(Vs + vrow * ATT_LD + (jd + (m >> 1)) * 8));
-      mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
-      mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
-    }
-  }
-
-  // ---- normalise and store (bf16x2 per thread per 8-wide dh tile)
-#pragma unroll
-  for (int jd = 0; jd < 8; ++jd) {
-    const int col = h * ATT_DH + jd * 8 + 2 * tq;
-    if (qr0 < T)
-      *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + qr0) * D + col) = pack_bf16x2(o[jd][0] * inv0, o[jd][1] * inv0);
-    if (qr1 < T)
-      *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + qr1) * D + col) = pack_bf16x2(o[jd][2] * inv1, o[jd][3] * inv1);
-  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,8 +332,5 @@ __global__ void probe_query_kernel(const float* __restrict__ W, const float* __r
   a = warp_sum(a);
   if (lane == 0) q[n] = (a + bias[n]) * scale;
 }
-
-template <int TPAD, int QW>
-constexpr int attention_smem_bytes() { return (2 * TPAD + QW * 16) * ATT_LD * 2 + TPAD; }
 
 }  // namespace mmcm

@@ -230,10 +230,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll 1
           for (int c = 0; c < HALF_N / 64; ++c) {
             uint32_t r0[32], r1[32];
+            const bool tr = (e == 0 && lane == 0 && tile == pair);
+            if (tr && c == 0) trace_stamp(ep, 10);
             tmem_ld32(t_row + (uint32_t)(c * 64), r0);
             tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r1);
             tmem_ld_wait();
+            if (tr && c == 0) trace_stamp(ep, 11);
             epi_chunk_bf16<EPI>(ep, stage_smem, bias_smem + c * 256, lane, row_base, col_base + c * 64, M, r0, r1);
+            if (tr && c == 0) trace_stamp(ep, 12);
+            if (tr && c == 1) trace_stamp(ep, 13);
           }
         } else {
 #pragma unroll

@@ -32,6 +32,7 @@
 #include "gemm2_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "heads.cuh"
+#include "prepost.cuh"
 #include "rowwise.cuh"
 
 using namespace mmcm;
@@ -59,6 +60,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 static int g_num_sms = kNumSMs;
+static int g_pair_limit = 0;   // > 0: cap the CTA pairs a GEMM launch may occupy (SM partitioning between the towers)
 
 // cudaFuncSetAttribute is per device: remember which devices a given kernel instantiation was configured on
 struct AttrOnce {
@@ -206,7 +208,8 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
   static AttrOnce once;
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
-  const int pairs = g_num_sms / 2;
+  int pairs = g_num_sms / 2;
+  if (g_pair_limit > 0 && g_pair_limit < pairs) pairs = g_pair_limit;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, ep, M, N, K));   // __cluster_dims__(2,1,1) on the kernel
   CK(cudaGetLastError());
@@ -284,14 +287,21 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
 template <int TPAD, int QW>
 static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, int T, int heads, int causal,
                       cudaStream_t st, const int* seq_start, const int* seq_len) {
+  using C = AttCfg<TPAD, QW>;
   auto kern = attention_kernel<TPAD, QW>;
-  constexpr int smem = attention_smem_bytes<TPAD, QW>();
   static AttrOnce once;
-  if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int qblocks = (TPAD / 16 + QW - 1) / QW;
-  dim3 grid(heads, B, qblocks);
-  CK(launch_k(kern, dim3(grid), dim3(QW * 32), smem, st, qkv, out, kvalid, seq_start, seq_len, T, heads * ATT_DH, causal, T));
-  CK(cudaGetLastError());
+  static int ctas_per_sm = 1;
+  if (once.need()) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    int n = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, QW * 32, C::SMEM_BYTES));
+    ctas_per_sm = n > 0 ? n : 1;
+  }
+  const int total = B * heads * C::QBLOCKS;
+  int grid = g_num_sms * ctas_per_sm;
+  if (grid > total) grid = total;
+  CK(launch_k(kern, dim3(grid), dim3(QW * 32), C::SMEM_BYTES, st, qkv, out, kvalid, seq_start, seq_len, T, heads * ATT_DH,
+              causal, T, B, heads));
   return MMCM_OK;
 }
 
@@ -409,6 +419,7 @@ struct mmcm_handle_s {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int warm = 0; };
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
   int opt_graph_max_batch = 0;   // off by default: small batches are bound by the GPU-side kernel chain, not the host
+  int opt_pairs_text = 0, opt_pairs_vis = 0;   // > 0: CTA pairs the text / vision GEMMs may occupy (two-stream SM split)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   int last_chunk_text = 0, last_chunk_vis = 0;
@@ -812,7 +823,10 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
     else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
     e->stats.launches++;
   }
-  CKR(run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr));
+  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_text : 0;
+  const int rl = run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr);
+  g_pair_limit = 0;
+  CKR(rl);
   // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
   CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
   e->last_text_rows = rows;
@@ -844,7 +858,10 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
     S->launches++;
     CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
   }
-  CKR(run_layers(e, t, a, rows, n, T, nullptr, 0, st));
+  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_vis : 0;
+  const int rl = run_layers(e, t, a, rows, n, T, nullptr, 0, st);
+  g_pair_limit = 0;
+  CKR(rl);
   if (clip) {
     CK(launch_k(fill_pool_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a.pool_row, n, T, 0));
     CK(cudaGetLastError());
@@ -1205,8 +1222,10 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   CK(cudaMemcpyAsync(e->d_tp, text_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_ip, image_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min((int)B, e->opt_micro_batch);
-  const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, e->opt_micro_batch, g_num_sms)
-                                   : std::min((int)B, e->opt_micro_batch);
+  // the vision chunks double as the H2D pipeline stages (pixels are 602 KB/sample): keep them <= 256 samples so that
+  // the copy of chunk i+1 overlaps the towers of chunk i; the text tower does not wait for pixels at all
+  const int vcap = std::min(e->opt_micro_batch, 256);
+  const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, vcap, g_num_sms) : std::min((int)B, vcap);
   e->last_chunk_text = ct; e->last_chunk_vis = cv;
   CKR(ensure_arenas(e, ct, cv));
   CKR(ensure_batch(e, B));
@@ -1326,6 +1345,10 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
+  else if (n == "pairs_text" || n == "pairs_vision") {
+    if (value < 0 || value > 74) return fail(MMCM_EINVAL, "%s must be in [0, 74]", name);
+    (n == "pairs_text" ? h->opt_pairs_text : h->opt_pairs_vis) = (int)value;
+  }
   else if (n == "graph_max_batch") {
     if (value < 0 || value > 4096) return fail(MMCM_EINVAL, "graph_max_batch out of range");
     h->opt_graph_max_batch = (int)value;
@@ -1367,6 +1390,30 @@ int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B, int32_t
   if (T <= 0 || heads <= 0) return fail(MMCM_EINVAL, "bad T/heads");
   return launch_attention(reinterpret_cast<const bf16*>(qkv), key_valid, B, T, heads, causal,
                           reinterpret_cast<bf16*>(out), reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_preprocess_u8(const uint8_t* hwc, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3,
+                       float* chw_out, void* stream) {
+  if (!hwc || !chw_out || !mean3 || !std3) return fail(MMCM_EINVAL, "null pointer");
+  if (B < 0 || H <= 0 || W <= 0 || (W & 3)) return fail(MMCM_EINVAL, "preprocess_u8: need W %% 4 == 0 (got %dx%d)", H, W);
+  if (B == 0) return MMCM_OK;
+  const int64_t total = (int64_t)B * 3 * H * (W / 4);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  CK(launch_k(preprocess_u8_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), hwc, chw_out, B, H, W,
+              mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]));
+  return MMCM_OK;
+}
+
+int mmcm_postprocess(const float* logits, const float* thresholds, const float* labels, int32_t B, int32_t C,
+                     float* probs_out, uint8_t* decisions_out, uint8_t* any_out, uint64_t* confusion_accum,
+                     void* stream) {
+  if (!logits || !thresholds) return fail(MMCM_EINVAL, "null pointer");
+  if (B < 0 || C <= 0 || C > POST_MAXC) return fail(MMCM_EINVAL, "postprocess: need 0 < C <= %d", POST_MAXC);
+  if (B == 0) return MMCM_OK;
+  CK(launch_k(postprocess_kernel, dim3((B + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), logits,
+              thresholds, labels, B, C, probs_out, decisions_out, any_out,
+              reinterpret_cast<unsigned long long*>(confusion_accum)));
+  return MMCM_OK;
 }
 
 int mmcm_cast_bf16(const float* src, void* dst, int64_t n, float scale, void* stream) {

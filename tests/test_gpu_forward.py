@@ -227,3 +227,23 @@ def test_packed_varlen_text_is_bit_identical_to_dense(name):
                      batch["image_present"])
     assert torch.equal(p_, d)
     eng.close()
+
+
+@pytest.mark.parametrize("B,S", [(1, 77), (2, 5), (3, 1), (5, 33)])
+def test_tiny_batches_and_short_sequences(B, S):
+    """The online path (scripts/inference.py builds B=1 batches) and S < 77 (any S <= max positions is legal)."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    full = syn.make_inputs(a, max(B, 8), seed=40 + B)
+    batch = {k: v[:B].contiguous() for k, v in full.items()}
+    batch["input_ids"] = batch["input_ids"][:, :S].contiguous()
+    batch["attention_mask"] = batch["attention_mask"][:, :S].contiguous()
+    with torch.no_grad():
+        ref = oracle_forward(kind, a, sd, batch)
+    for varlen in (1, 0):
+        m.set_option("varlen_text", varlen)
+        got = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
+        assert got.shape == (B, 5)
+        err = (got - ref).abs().max().item()
+        assert err <= 0.05 * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # 5 % of the hardened logit spread

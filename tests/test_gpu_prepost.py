@@ -1,0 +1,64 @@
+"""uint8 pre-processing and fused post-processing against the oracle (the reference's literal
+numpy / sklearn expressions)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_preprocess_u8_is_bit_identical_to_totensor_normalize():
+    from mmcm_b200 import prepost
+    from oracle import prepost_oracle as orc
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (5, 224, 224, 3), generator=g, dtype=torch.uint8)
+    for mean, std in (([0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]),   # CLIP processor
+                      ([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])):                                             # SigLIP / default
+        ref = orc.to_tensor_normalize(img, mean, std)
+        got = prepost.preprocess_u8(img.cuda(), mean, std).cpu()
+        assert got.shape == (5, 3, 224, 224)
+        assert torch.equal(got, ref)
+
+
+def test_postprocess_matches_numpy_and_sklearn():
+    from mmcm_b200 import prepost
+    from oracle import prepost_oracle as orc
+    g = torch.Generator().manual_seed(1)
+    B, C = 4099, 5
+    logits = torch.randn(B, C, generator=g) * 3
+    thr = torch.tensor([0.2, 0.35, 0.5, 0.8, 0.95])            # R/runs/*/inference_config.json range
+    y = (torch.rand(B, C, generator=g) < 0.3).float()
+    p_ref, l_ref, a_ref = orc.postprocess(logits.numpy(), thr.numpy())
+    out = prepost.postprocess(logits.cuda(), thr, labels=y)
+    probs = out["probs"].cpu().numpy()
+    np.testing.assert_allclose(probs, p_ref, rtol=0, atol=2e-7)
+    safe = np.abs(p_ref - thr.numpy()[None]) > 1e-6              # decisions are exact away from a 1-ulp band
+    assert (out["labels"].cpu().numpy() == l_ref)[safe].all()
+    rows_safe = safe.all(axis=1)
+    assert (out["any_harmful"].cpu().numpy() == a_ref)[rows_safe].all()
+    conf = out["confusion"]
+    assert int(conf.sum()) == B * C
+    # accumulate a second batch into the same counters, then compare the derived metrics with sklearn on both
+    out2 = prepost.postprocess(logits.flip(0).cuda(), thr, labels=y.flip(0), confusion=conf)
+    m = prepost.metrics_from_confusion(out2["confusion"])
+    ref = orc.detailed_metrics(np.concatenate([p_ref, p_ref[::-1]]), np.concatenate([y.numpy(), y.numpy()[::-1]]),
+                               thr.numpy())
+    for k in ("f1_macro", "f1_micro", "precision_macro", "recall_macro"):
+        assert abs(m[k] - ref[k]) < 1e-9, k
+    np.testing.assert_allclose(m["per_class"]["f1"], ref["per_class_f1"], atol=1e-9)
+
+
+def test_u8_pipeline_feeds_the_forward():
+    """uint8 images -> preprocess_u8 -> model == fp32 pixel_values computed the reference's way -> model."""
+    from conftest import build_case
+    from test_gpu_forward import _make_module
+    from mmcm_b200 import prepost, synthetic as syn
+    from oracle import prepost_oracle as orc
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 8, seed=50).items()}
+    img = torch.randint(0, 256, (8, 224, 224, 3), generator=torch.Generator().manual_seed(2), dtype=torch.uint8)
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    b_ref = dict(batch, pixel_values=orc.to_tensor_normalize(img, mean, std).cuda())
+    b_u8 = dict(batch, pixel_values=prepost.preprocess_u8(img.cuda(), mean, std))
+    assert torch.equal(m(**b_ref)["logits"], m(**b_u8)["logits"])

@@ -37,9 +37,14 @@ t = trace.view(148, 16).cpu()
 names = ["entry", "prologue", "first data", "tile0 mma issued", "tile0 acc ready", "tile0 epi done", "last mma issued",
          "last acc ready", "last epi done", "exit"]
 t0 = t[:, 0].min().item()
-print(f"M={M} N={N} K={K} epi={epi}: clock64 cycles relative to the earliest CTA entry (leader CTAs 0, 2, 72, 146; peer 1)")
+print(f"M={M} N={N} K={K} epi={epi}: clock64 cycles relative to each CTA's own entry (leader CTAs 0, 2, 72, 146; peer 1)")
 for cta in (0, 2, 72, 146, 1):
     row = t[cta]
-    print(f"cta {cta:3d}: " + "  ".join(f"{names[i]}={row[i].item() - t0 if row[i].item() else -1}" for i in range(10)))
+    print(f"cta {cta:3d}: " + "  ".join(f"{names[i]}={row[i].item() - row[0].item() if row[i].item() else -1}" for i in range(10)))
+for cta in (0, 2, 72):
+    row = t[cta]
+    print(f"cta {cta}: epilogue warp 0, tile 0: ldtm issue->ready {row[11].item() - row[10].item()}  chunk0 math+store "
+          f"{row[12].item() - row[11].item()}  chunk1 total {row[13].item() - row[12].item()}  "
+          f"(acc ready -> first ldtm {row[10].item() - row[4].item()})")
 ex = t[:, 9] - t0
 print("exit stamp over CTAs: min", ex.min().item(), "max", ex.max().item(), " entry spread", (t[:, 0] - t0).max().item())

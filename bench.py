@@ -196,6 +196,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     if kind == "fusion":
@@ -312,7 +314,10 @@ def main():
         achieved = gfl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all encoder GEMMs of one step, CUDA events per launch)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"], "gemm_launches": gn, "gemm_ms_per_step": gms,
+                # DRAM bytes per GEMM launch, mean over the 4 encoder GEMMs of a text layer at chunk 1024, from the
+                # `ncu --set full` capture profiles/r01_gemm_pair_ncu_full.txt (qkv 267 MB, out 351 MB, fc1 350 MB,
+                # fc2 625 MB; algorithmic operand+result bytes of the same launches: 325, 403, 406, 728 MB)
+                "traffic": 398e6 if args.model.startswith("clip") else None, "peak_source": peaks["source"], "gemm_launches": gn, "gemm_ms_per_step": gms,
                 "gemm_flops_per_step": gfl,
                 "model_algorithmic_tflops": value / world * flops["total"] / 1e12,
                 "model_frac_of_peak": value / world * flops["total"] / 1e12 / peaks["tflops"]}

@@ -76,14 +76,20 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
   static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 6 : 8;
+#ifndef MMCM_PAIR_STAGES
+#define MMCM_PAIR_STAGES 6
+#endif
+#ifndef MMCM_PAIR_REG_THREADS
+#define MMCM_PAIR_REG_THREADS 384   /* __launch_bounds__ thread count used only to cap registers per thread */
+#endif
+  static constexpr int STAGES = (BLOCK_N == 256) ? MMCM_PAIR_STAGES : MMCM_PAIR_STAGES + 2;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
 };
 
 template <int BLOCK_N, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BLOCK_N>::THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMCM_PAIR_REG_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const EpiParams ep, const int M_host, const int N, const int K) {
   using C = Gemm2Cfg<BLOCK_N>;
@@ -229,14 +235,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (!kF32) {
 #pragma unroll 1
           for (int c = 0; c < HALF_N / 64; ++c) {
-            uint32_t r0[32], r1[32];
             const bool tr = (e == 0 && lane == 0 && tile == pair);
             if (tr && c == 0) trace_stamp(ep, 10);
-            tmem_ld32(t_row + (uint32_t)(c * 64), r0);
-            tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r1);
-            tmem_ld_wait();
-            if (tr && c == 0) trace_stamp(ep, 11);
-            epi_chunk_bf16<EPI>(ep, stage_smem, bias_smem + c * 256, lane, row_base, col_base + c * 64, M, r0, r1);
+            uint32_t w[32];
+            {
+              uint32_t r[32];
+              tmem_ld32(t_row + (uint32_t)(c * 64), r);
+              tmem_ld_wait();
+              if (tr && c == 0) trace_stamp(ep, 11);
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256, r, &w[0]);
+            }
+            {
+              uint32_t r[32];
+              tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r);
+              tmem_ld_wait();
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16]);
+            }
+            epi_store_bf16(ep, stage_smem, lane, row_base, col_base + c * 64, M, w);
             if (tr && c == 0) trace_stamp(ep, 12);
             if (tr && c == 1) trace_stamp(ep, 13);
           }
@@ -244,15 +259,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
           for (int c = 0; c < HALF_N / 32; ++c) {
             uint32_t r[32];
-            float4 xn[8];
             tmem_ld32(t_row + (uint32_t)(c * 32), r);
-            if (c + 1 < HALF_N / 32) epi_load_addend<EPI>(ep, lane, row_base, col_base + (c + 1) * 32, M, xn);
             tmem_ld_wait();
             epi_chunk_f32<EPI>(ep, stage_smem, lane, row_base, col_base + c * 32, M, r, xa, fb[c]);
-            if (c + 1 < HALF_N / 32) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) xa[i] = xn[i];
-            }
+            if (c + 1 < HALF_N / 32) epi_load_addend<EPI>(ep, lane, row_base, col_base + (c + 1) * 32, M, xa);
           }
         }
       }

@@ -137,6 +137,58 @@ __device__ __forceinline__ void epi_chunk_bf16(const EpiParams& ep, const uint32
   }
 }
 
+// the same epilogue in two steps, for callers that want only 32 accumulator registers live at a time:
+// pack 32 fp32 accumulators (+ bias from smem, + activation) into 16 bf16x2 words ...
+template <int EPI>
+__device__ __forceinline__ void epi_pack_bf16(const EpiParams& ep, const uint32_t bias_smem, const uint32_t (&r)[32],
+                                              uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * i + j]);
+    const uint4 ba = lds128(bias_smem + i * 32), bb = lds128(bias_smem + i * 32 + 16);
+    v[0] += __uint_as_float(ba.x); v[1] += __uint_as_float(ba.y); v[2] += __uint_as_float(ba.z); v[3] += __uint_as_float(ba.w);
+    v[4] += __uint_as_float(bb.x); v[5] += __uint_as_float(bb.y); v[6] += __uint_as_float(bb.z); v[7] += __uint_as_float(bb.w);
+    if (EPI == EPI_BIAS_ACT_BF16) {
+      if (ep.act == ACT_QUICK_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = quick_gelu_fast(v[j]);
+      } else if (ep.act == ACT_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);
+      }
+    }
+    w[4 * i + 0] = pack_bf16x2(v[0], v[1]);
+    w[4 * i + 1] = pack_bf16x2(v[2], v[3]);
+    w[4 * i + 2] = pack_bf16x2(v[4], v[5]);
+    w[4 * i + 3] = pack_bf16x2(v[6], v[7]);
+  }
+}
+// ... then transpose 32 rows x 64 bf16 columns (w[32] per lane) through the staging tile and store full lines
+__device__ __forceinline__ void epi_store_bf16(const EpiParams& ep, const uint32_t stage, const int lane,
+                                               const int row_base, const int col0, const int M, const uint32_t (&w)[32]) {
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+  const int sub = lane >> 3, c16 = lane & 7;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((lane >> 4) == pass) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        sts128(stage + (lane & 15) * EPI_PITCH + i * 16, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rl = it * 4 + sub;
+      const uint4 v = lds128(stage + rl * EPI_PITCH + c16 * 16);
+      const int row = row_base + pass * 16 + rl;
+      if (row < M) *reinterpret_cast<uint4*>(out + (size_t)row * ep.ldo + col0 + c16 * 8) = v;
+    }
+    __syncwarp();
+  }
+}
+
 // fp32 outputs: 32 columns starting at col0.  The addend (residual stream or position embedding) of a chunk is 8
 // float4 per lane; it is loaded by `epi_load_addend` BEFORE the accumulator is waited for (the residual may alias
 // the output, so the compiler cannot hoist these loads above earlier stores by itself -- a load->store->load chain

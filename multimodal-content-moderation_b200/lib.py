@@ -72,9 +72,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
-        path = _build.build_library()
+    path = os.environ.get("MMCM_LIB_PATH")      # dev: A/B a differently built library
+    if not path:
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            path = _build.build_library()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: the CUDA extension is mandatory (no CPU fallback)")
     lib = C.CDLL(path)

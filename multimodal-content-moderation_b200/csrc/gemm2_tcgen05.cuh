@@ -66,6 +66,27 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
+// ---- TMA store epilogue ------------------------------------------------------------------------------
+// The per-thread STG read-back of the first pair kernel cost 1.4-1.9 k cycles per 32x64 chunk per warp
+// (tools/gemm_trace.py): the SM's LSU store path, not the math, bounded the K=512 GEMMs.  Here a warp writes its
+// 32 rows x 128 B chunk into a 128B-swizzled staging tile (conflict free: 16-byte slot i of row r goes to slot
+// i ^ (r & 7)) and ONE lane hands it to the TMA unit:
+//   bf16 outputs : cp.async.bulk.tensor.2d.global.shared::cta          (plain tile store)
+//   fp32 residual: cp.reduce.async.bulk.tensor.2d ... .add.f32          (x += acc + bias inside L2: the residual
+//                  stream is never read into the SM, and fp32 addition is commutative so the result is identical)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+constexpr int EPI_TMA_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled, 1 KB aligned
+
 template <int BLOCK_N>
 struct Gemm2Cfg {
   static constexpr int BLOCK_M = 256;           // per pair; 128 rows per CTA
@@ -77,13 +98,13 @@ struct Gemm2Cfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;
 #ifndef MMCM_PAIR_STAGES
-#define MMCM_PAIR_STAGES 6
+#define MMCM_PAIR_STAGES 5   /* 4 stages already saturate the TMA->UMMA loop (tools/mainloop_probe.cu) */
 #endif
 #ifndef MMCM_PAIR_REG_THREADS
 #define MMCM_PAIR_REG_THREADS 384   /* __launch_bounds__ thread count used only to cap registers per thread */
 #endif
   static constexpr int STAGES = (BLOCK_N == 256) ? MMCM_PAIR_STAGES : MMCM_PAIR_STAGES + 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_TMA_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
 };
@@ -91,7 +112,8 @@ struct Gemm2Cfg {
 template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMCM_PAIR_REG_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const EpiParams ep, const int M_host, const int N, const int K) {
+                     const __grid_constant__ CUtensorMap tmap_c, const EpiParams ep, const int M_host, const int N,
+                     const int K, const int tma_out) {
   using C = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES];    // used in the leader only
@@ -115,6 +137,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (tma_out) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -200,8 +223,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // ===================== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====================
     const int e = warp - 4;
     const int lg = e & 3, ch = e >> 2;
-    const uint32_t stage_smem = epi_base + e * EPI_STAGE_BYTES;
-    const uint32_t bias_smem = epi_base + C::EPI_WARPS * EPI_STAGE_BYTES + e * C::EPI_BIAS_BYTES;
+    const uint32_t stage_smem = epi_base + e * EPI_TMA_STAGE_BYTES;   // 1 KB aligned (epi_base is, 4 KB per warp)
+    const uint32_t bias_smem = epi_base + C::EPI_WARPS * EPI_TMA_STAGE_BYTES + e * C::EPI_BIAS_BYTES;
+    const bool tma_path = tma_out != 0 && EPI != EPI_PATCH_F32;
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr bool kF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32);
     int as = 0;
@@ -212,7 +236,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int col_base = n_blk * BLOCK_N + ch * HALF_N;
       float4 xa[8];
       float4 fb[HALF_N / 32];
-      if (kF32) {
+      if (kF32 && !tma_path) {
 #pragma unroll
         for (int c = 0; c < HALF_N / 32; ++c)
           fb[c] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base + c * 32 + (lane & 7) * 4))
@@ -251,9 +275,49 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               tmem_ld_wait();
               epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16]);
             }
-            epi_store_bf16(ep, stage_smem, lane, row_base, col_base + c * 64, M, w);
+            if (tr && c == 0) trace_stamp(ep, 14);
+            if (tma_path) {
+              if (lane == 0) bulk_wait_read0();            // the previous chunk's store has finished reading the tile
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                sts128(stage_smem + lane * 128 + ((i ^ (lane & 7)) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+              fence_proxy_async();                          // generic-proxy writes -> visible to the TMA unit
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_c, stage_smem, col_base + c * 64, row_base);
+                bulk_commit();
+              }
+            } else {
+              epi_store_bf16(ep, stage_smem, lane, row_base, col_base + c * 64, M, w);
+            }
             if (tr && c == 0) trace_stamp(ep, 12);
             if (tr && c == 1) trace_stamp(ep, 13);
+          }
+        } else if (tma_path) {
+#pragma unroll 1
+          for (int c = 0; c < HALF_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 b = lds128(bias_smem + c * 128 + i * 16);
+              sts128(stage_smem + lane * 128 + ((i ^ (lane & 7)) << 4),
+                     __float_as_uint(__uint_as_float(r[4 * i]) + __uint_as_float(b.x)),
+                     __float_as_uint(__uint_as_float(r[4 * i + 1]) + __uint_as_float(b.y)),
+                     __float_as_uint(__uint_as_float(r[4 * i + 2]) + __uint_as_float(b.z)),
+                     __float_as_uint(__uint_as_float(r[4 * i + 3]) + __uint_as_float(b.w)));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (ep.resid) tma_reduce_add_2d(&tmap_c, stage_smem, col_base + c * 32, row_base);   // x += acc + bias
+              else tma_store_2d(&tmap_c, stage_smem, col_base + c * 32, row_base);
+              bulk_commit();
+            }
           }
         } else {
 #pragma unroll
@@ -273,6 +337,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (tma_path && lane == 0) bulk_wait0();   // all bulk stores of this warp are complete (globally visible)
   }
 
   if (threadIdx.x == 0) trace_stamp(ep, 9);

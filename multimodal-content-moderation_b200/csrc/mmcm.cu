@@ -135,9 +135,24 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, i
 struct TmapKey {
   const void* p;
   int64_t rows, K;
-  int box;
+  int box;   // operand maps: box rows; output maps: -1 (bf16 64x32 box) / -2 (fp32 32x32 box)
   bool operator<(const TmapKey& o) const { return std::tie(p, rows, K, box) < std::tie(o.p, o.rows, o.K, o.box); }
 };
+
+// output tile map for the TMA-store epilogue: row-major [rows, ld] bf16 or fp32, box = 128 bytes x 32 rows, 128B swizzle
+static int make_out_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, bool f32) {
+  const int esz = f32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMCM_ECUDA, "cuTensorMapEncodeTiled(out) failed (%d) rows=%lld ld=%lld", (int)r,
+                                     (long long)rows, (long long)ld);
+  return MMCM_OK;
+}
 static std::map<TmapKey, CUtensorMap> g_tmaps;
 
 static int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box, bool weight) {
@@ -146,7 +161,8 @@ static int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, 
   auto it = g_tmaps.find(k);
   if (it == g_tmaps.end()) {
     CUtensorMap m;
-    CKR(make_tmap(&m, ptr, rows, K, box, weight));
+    if (box < 0) CKR(make_out_tmap(&m, ptr, rows, K, box == -2));
+    else CKR(make_tmap(&m, ptr, rows, K, box, weight));
     if (g_tmaps.size() > 8192) g_tmaps.clear();
     it = g_tmaps.emplace(k, m).first;
   }
@@ -200,6 +216,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
   return MMCM_OK;
 }
 
+static bool g_tma_epilogue = true;
 template <int BN, int EPI>
 static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, int M, int N, int K,
                           cudaStream_t st) {
@@ -211,7 +228,15 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
   int pairs = g_num_sms / 2;
   if (g_pair_limit > 0 && g_pair_limit < pairs) pairs = g_pair_limit;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, ep, M, N, K));   // __cluster_dims__(2,1,1) on the kernel
+  // TMA-store epilogue: bf16 tile stores; fp32 residual GEMMs as an L2 reduce-add (needs resid == out or no resid);
+  // rows / pitches must keep the 16-byte global alignment TMA wants.  Otherwise the per-thread store path is used.
+  constexpr bool f32 = (EPI == EPI_BIAS_RESID_F32);
+  int tma_out = g_tma_epilogue && EPI != EPI_PATCH_F32 && (ep.ldo * (f32 ? 4 : 2)) % 16 == 0 &&
+                (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  if (f32 && ep.resid && ep.resid != ep.out) tma_out = 0;
+  CUtensorMap tc = ta;
+  if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
+  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -1341,7 +1366,8 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "streams") {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
-  } else if (n == "pdl") g_pdl = value != 0;   // process-wide: programmatic dependent launch on/off
+  } else if (n == "pdl") g_pdl = value != 0;
+  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;   // process-wide: TMA store / reduce-add epilogue of the pair GEMM   // process-wide: programmatic dependent launch on/off
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;

@@ -45,6 +45,7 @@ for cta in (0, 2, 72):
     row = t[cta]
     print(f"cta {cta}: epilogue warp 0, tile 0: ldtm issue->ready {row[11].item() - row[10].item()}  chunk0 math+store "
           f"{row[12].item() - row[11].item()}  chunk1 total {row[13].item() - row[12].item()}  "
-          f"(acc ready -> first ldtm {row[10].item() - row[4].item()})")
+          f"(acc ready -> first ldtm {row[10].item() - row[4].item()})  chunk0: 2xLDTM+pack {row[14].item() - row[10].item()} "
+          f"store passes {row[12].item() - row[14].item()}")
 ex = t[:, 9] - t0
 print("exit stamp over CTAs: min", ex.min().item(), "max", ex.max().item(), " entry spread", (t[:, 0] - t0).max().item())

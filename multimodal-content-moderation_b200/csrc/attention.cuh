@@ -50,6 +50,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 2^x as ONE MUFU: exp2f() wraps ex2.approx in denormal range fix-ups (2 FMUL + compare + select per call), which
+// the softmax does not need -- arguments are <= 0 and a flushed 2^-127 contributes nothing to a sum that contains 1
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int TPAD, int QW>
 struct AttCfg {
   static constexpr int QROWS = QW * 16;
@@ -183,16 +191,24 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
+        // warp-uniform fast path: all 8 keys of the tile are valid and (if causal) not after this warp's first row
+        const uint32_t tile_bits = (vmask[(j * 8) / 32] >> ((j * 8) & 31)) & 0xffu;
+        const bool full = tile_bits == 0xffu && (!causal || j * 8 + 7 <= r0);
+        if (full) {
+          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        } else {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int key = j * 8 + 2 * tq + e;
-          const bool kok = (vmask[(j * 8) / 32] >> (key & 31)) & 1u;
-          const bool ok0 = kok && (!causal || key <= qr0);
-          const bool ok1 = kok && (!causal || key <= qr1);
-          s[j][e] = ok0 ? s[j][e] : -INFINITY;
-          s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
-          mx0 = fmaxf(mx0, s[j][e]);
-          mx1 = fmaxf(mx1, s[j][2 + e]);
+          for (int e = 0; e < 2; ++e) {
+            const int key = j * 8 + 2 * tq + e;
+            const bool kok = (tile_bits >> (2 * tq + e)) & 1u;
+            const bool ok0 = kok && (!causal || key <= qr0);
+            const bool ok1 = kok && (!causal || key <= qr1);
+            s[j][e] = ok0 ? s[j][e] : -INFINITY;
+            s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
+            mx0 = fmaxf(mx0, s[j][e]);
+            mx1 = fmaxf(mx1, s[j][2 + e]);
+          }
         }
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
@@ -206,10 +222,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        s[j][0] = exp2f(fmaf(s[j][0], L2E, nm0));
-        s[j][1] = exp2f(fmaf(s[j][1], L2E, nm0));
-        s[j][2] = exp2f(fmaf(s[j][2], L2E, nm1));
-        s[j][3] = exp2f(fmaf(s[j][3], L2E, nm1));
+        s[j][0] = ex2_fast(fmaf(s[j][0], L2E, nm0));
+        s[j][1] = ex2_fast(fmaf(s[j][1], L2E, nm0));
+        s[j][2] = ex2_fast(fmaf(s[j][2], L2E, nm1));
+        s[j][3] = ex2_fast(fmaf(s[j][3], L2E, nm1));
         sum0 += s[j][0] + s[j][1];
         sum1 += s[j][2] + s[j][3];
       }

@@ -247,3 +247,19 @@ def test_tiny_batches_and_short_sequences(B, S):
         assert got.shape == (B, 5)
         err = (got - ref).abs().max().item()
         assert err <= 0.05 * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # 5 % of the hardened logit spread
+
+
+def test_two_models_in_one_process_do_not_interfere():
+    """Two handles (Fusion + MTL) share the process-wide TMA-descriptor cache and tile-scheduler state."""
+    from mmcm_b200 import synthetic as syn
+    k1, a1, kw1, sd1, _, _ = build_case("clip_fusion_hardened")
+    k2, a2, kw2, sd2, _, _ = build_case("clip_mtl_h256_hardened")
+    m1, m2 = _make_module(k1, a1, kw1, sd1), _make_module(k2, a2, kw2, sd2)
+    b = {k: v.to("cuda:0") for k, v in syn.make_inputs(a1, 24, seed=60, edge_rows=True).items()}
+    y1, y2 = m1(**b)["logits"].clone(), m2(**b)["logits"].clone()
+    for _ in range(3):
+        assert torch.equal(m2(**b)["logits"], y2)
+        assert torch.equal(m1(**b)["logits"], y1)
+    del m1
+    torch.cuda.synchronize()
+    assert torch.equal(m2(**b)["logits"], y2)      # destroying one handle (clears the descriptor cache) is harmless

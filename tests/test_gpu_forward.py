@@ -263,3 +263,25 @@ def test_two_models_in_one_process_do_not_interfere():
     del m1
     torch.cuda.synchronize()
     assert torch.equal(m2(**b)["logits"], y2)      # destroying one handle (clears the descriptor cache) is harmless
+
+
+def test_config5_shard_size_properties():
+    """BASELINE config 5: 22.5 k samples over 8 GPUs = 2812-sample shards.  Size-independent properties at that size:
+    finite, invariant to the internal micro-batching, identical for packed and dense text, equal to a small-batch run
+    on a slice (samples are independent)."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    B = 2812
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, B, seed=70).items()}
+    y = m(**batch)["logits"].clone()
+    assert y.shape == (B, 5) and torch.isfinite(y).all()
+    m.set_option("micro_batch", 333)
+    assert torch.equal(m(**batch)["logits"], y)
+    m.set_option("varlen_text", 0)
+    assert torch.equal(m(**batch)["logits"], y)
+    m.set_option("varlen_text", 1)
+    m.set_option("micro_batch", 1024)
+    sl = slice(1000, 1064)
+    ys = m(**{k: v[sl].contiguous() for k, v in batch.items()})["logits"]
+    assert torch.equal(ys, y[sl])

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -28,6 +29,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "gemm2_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
@@ -318,9 +320,11 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
   static int ctas_per_sm = 1;
   if (once.need()) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int n = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, QW * 32, C::SMEM_BYTES));
     ctas_per_sm = n > 0 ? n : 1;
+    if (getenv("MMCM_DEBUG")) fprintf(stderr, "[mmcm] attention<%d,%d>: occupancy %d CTAs/SM\n", TPAD, QW, n);
   }
   const int total = B * heads * C::QBLOCKS;
   int grid = g_num_sms * ctas_per_sm;
@@ -330,10 +334,48 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
   return MMCM_OK;
 }
 
+static long long* g_gemm_trace = nullptr;   // dev tool, see mmcm_debug_set_gemm_trace
+// 0 = auto: tcgen05 kernel when at least two samples share a 128-row tile (T <= 64: measured 80 vs 87 us for the
+// 50-token vision tower), mma.sync kernel otherwise (77-token text: 90 vs 98 us); 1 = always mma.sync; 2 = tcgen05
+// whenever T <= 128
+static int g_attention_impl = 0;
+
+static int launch_attention_tc(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
+                               cudaStream_t st, const int* seq_start, const int* seq_len) {
+  CKR(ensure_driver());
+  static AttrOnce once;
+  if (once.need()) {
+    CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  // 49 KB of shared memory and 128 of the SM's 512 TMEM columns per CTA -> 4 resident CTAs per SM.  (The occupancy
+  // calculator answers 1 for a kernel that allocates TMEM; the hardware does co-schedule them: 247 -> 142 -> 98 us
+  // for 1 / 2 / 4 CTAs per SM, tools/attn_trace.py.)
+  int ctas_per_sm = 4;
+  if (getenv("MMCM_ATC_CTAS")) ctas_per_sm = atoi(getenv("MMCM_ATC_CTAS"));
+  const int D = heads * ATT_DH;
+  const int box_rows = seq_start ? 128 : T;          // one TMA box per sample slot
+  CUtensorMap tq;
+  CKR(get_tmap(&tq, qkv, (int64_t)B * T, 3 * D, box_rows, false));
+  const int slot = seq_start ? 128 : (T <= 16 ? 16 : (T <= 32 ? 32 : (T <= 64 ? 64 : 128)));
+  const int G = 128 / slot;
+  const int total = ((B + G - 1) / G) * heads;
+  int grid = g_num_sms * ctas_per_sm;
+  if (grid > total) grid = total;
+  CK(launch_k(attention_tc_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, out, kvalid, seq_start, seq_len, T, D,
+              causal, B, heads, box_rows, g_gemm_trace));
+  return MMCM_OK;
+}
+
 static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
                             cudaStream_t st, LaunchStats* stats, const int* seq_start = nullptr,
                             const int* seq_len = nullptr) {
   if (B <= 0) return MMCM_OK;
+  if ((g_attention_impl == 2 && T <= 128) || (g_attention_impl == 0 && T <= 64 && !seq_start)) {
+    CKR(launch_attention_tc(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
+    if (stats) stats->launches++;
+    return MMCM_OK;
+  }
   int r;
   if (T <= 16) r = launch_att<16, 1>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else if (T <= 32) r = launch_att<32, 2>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
@@ -695,6 +737,13 @@ static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) 
   CKR(dalloc(e, &a.seq_start, mb));
   CKR(dalloc(e, &a.seq_len, mb));
   CKR(dalloc(e, &a.rows_dev, 256));   // one live-row counter per packed chunk of a forward (accounting reads them back)
+  // TMA tiles of partially filled chunks also cover rows nobody wrote in this forward: they must hold finite numbers
+  // (a masked probability of 0 times a stale NaN in V would still be NaN)
+  CK(cudaMemset(a.x, 0, rows * t.D * sizeof(float)));
+  CK(cudaMemset(a.h, 0, rows * t.D * sizeof(bf16)));
+  CK(cudaMemset(a.qkv, 0, rows * 3 * t.D * sizeof(bf16)));
+  CK(cudaMemset(a.att, 0, rows * t.D * sizeof(bf16)));
+  CK(cudaMemset(a.ff, 0, rows * t.F * sizeof(bf16)));
   return MMCM_OK;
 }
 
@@ -1367,7 +1416,11 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
   } else if (n == "pdl") g_pdl = value != 0;
-  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;   // process-wide: TMA store / reduce-add epilogue of the pair GEMM   // process-wide: programmatic dependent launch on/off
+  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;
+  else if (n == "attention_impl") {
+    if (value < 0 || value > 2) return fail(MMCM_EINVAL, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05 for T <= 128)");
+    g_attention_impl = (int)value;
+  }   // process-wide: TMA store / reduce-add epilogue of the pair GEMM   // process-wide: programmatic dependent launch on/off
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
@@ -1384,7 +1437,6 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
 }
 
 // dev tool: per-CTA clock64 stamps of the CTA-pair GEMM (16 slots per CTA; see trace_stamp in gemm_tcgen05.cuh)
-static long long* g_gemm_trace = nullptr;
 int mmcm_debug_set_gemm_trace(void* device_buffer) {
   g_gemm_trace = reinterpret_cast<long long*>(device_buffer);
   return MMCM_OK;

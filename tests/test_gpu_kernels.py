@@ -152,7 +152,12 @@ def _ref_attention(qkv, B, T, H, causal, kvalid):
 @pytest.mark.parametrize("T,H,causal,masked", [
     (50, 12, 0, False), (77, 8, 1, False), (77, 8, 1, True), (64, 12, 0, True), (196, 12, 0, False),
     (11, 8, 1, True), (33, 8, 0, True), (128, 4, 1, True), (250, 2, 0, True)])
-def test_attention(lib, T, H, causal, masked):
+@pytest.mark.parametrize("impl", [1, 2])     # 1 = mma.sync kernel, 2 = tcgen05 kernel (T <= 128; falls back above)
+def test_attention(lib, T, H, causal, masked, impl):
+    import mmcm_b200 as P
+    from mmcm_b200 import arch as A
+    eng = P.Engine(A.CLIP_B32, A.HEAD_FUSION, 5)     # process-wide switch lives behind a handle's set_option
+    eng.set_option("attention_impl", impl)
     B = 6
     D = H * 64
     g = torch.Generator(device="cuda").manual_seed(T * 13 + H)
@@ -174,3 +179,5 @@ def test_attention(lib, T, H, causal, masked):
     assert (out.float() - ref).abs().max().item() < 3e-2
     if masked:
         assert (out.view(B, T, D)[0] == 0).all()
+    eng.set_option("attention_impl", 0)
+    eng.close()

@@ -99,11 +99,20 @@ def _encoder(x: Tensor, sd: SD, prefix: str, layers: int, heads: int, eps: float
     return x
 
 
+def _num_layers(sd: SD, prefix: str) -> int:
+    """Depth of the tower stored under `prefix` (so that truncated-depth test models need no extra arguments)."""
+    n = 0
+    while f"{prefix}encoder.layers.{n}.layer_norm1.weight" in sd:
+        n += 1
+    return n
+
+
 # ------------------------------------------------------------------------------------------ CLIP
 def clip_text_pooled(sd: SD, prefix: str, ids: Tensor, mask: Optional[Tensor], eos_id: int = 49407,
-                     heads: int = 8, layers: int = 12, eps: float = 1e-5,
+                     heads: int = 8, layers: Optional[int] = None, eps: float = 1e-5,
                      stages: Optional[dict] = None) -> Tensor:
     """CLIPTextTransformer.forward -> pooler_output (EOS row after final LN). prefix ends with 'text_model.'"""
+    layers = _num_layers(sd, prefix) if layers is None else layers
     B, S = ids.shape
     pos_w = sd[prefix + "embeddings.position_embedding.weight"]
     if S > pos_w.shape[0]:  # HF/models/clip/modeling_clip.py:243-247
@@ -124,9 +133,10 @@ def clip_text_pooled(sd: SD, prefix: str, ids: Tensor, mask: Optional[Tensor], e
     return x[torch.arange(B), idx]
 
 
-def clip_vision_pooled(sd: SD, prefix: str, px: Tensor, patch: int = 32, heads: int = 12, layers: int = 12,
-                       eps: float = 1e-5, stages: Optional[dict] = None) -> Tensor:
+def clip_vision_pooled(sd: SD, prefix: str, px: Tensor, patch: int = 32, heads: int = 12,
+                       layers: Optional[int] = None, eps: float = 1e-5, stages: Optional[dict] = None) -> Tensor:
     """CLIPVisionTransformer.forward -> pooler_output = post_layernorm(CLS). prefix ends with 'vision_model.'"""
+    layers = _num_layers(sd, prefix) if layers is None else layers
     w = sd[prefix + "embeddings.patch_embedding.weight"]
     B, _, H, W = px.shape
     pos_w = sd[prefix + "embeddings.position_embedding.weight"]
@@ -146,8 +156,9 @@ def clip_vision_pooled(sd: SD, prefix: str, px: Tensor, patch: int = 32, heads: 
 
 # ------------------------------------------------------------------------------------------ SigLIP
 def siglip_text_pooled(sd: SD, prefix: str, ids: Tensor, mask: Optional[Tensor], heads: int = 12,
-                       layers: int = 12, eps: float = 1e-6, stages: Optional[dict] = None) -> Tensor:
+                       layers: Optional[int] = None, eps: float = 1e-6, stages: Optional[dict] = None) -> Tensor:
     """SiglipTextTransformer.forward -> pooler_output = head(final_LN(x)[:, -1]); bidirectional key mask."""
+    layers = _num_layers(sd, prefix) if layers is None else layers
     B, S = ids.shape
     pos_w = sd[prefix + "embeddings.position_embedding.weight"]
     if S > pos_w.shape[0]:  # HF/models/siglip/modeling_siglip.py:211-215
@@ -163,9 +174,10 @@ def siglip_text_pooled(sd: SD, prefix: str, ids: Tensor, mask: Optional[Tensor],
     return _lin(x[:, -1], sd, prefix + "head")
 
 
-def siglip_vision_pooled(sd: SD, prefix: str, px: Tensor, patch: int = 16, heads: int = 12, layers: int = 12,
-                         eps: float = 1e-6, stages: Optional[dict] = None) -> Tensor:
+def siglip_vision_pooled(sd: SD, prefix: str, px: Tensor, patch: int = 16, heads: int = 12,
+                         layers: Optional[int] = None, eps: float = 1e-6, stages: Optional[dict] = None) -> Tensor:
     """SiglipVisionTransformer.forward -> MAP-pooled feature (HF/models/siglip/modeling_siglip.py:604-649)."""
+    layers = _num_layers(sd, prefix) if layers is None else layers
     w = sd[prefix + "embeddings.patch_embedding.weight"]
     b = sd[prefix + "embeddings.patch_embedding.bias"]
     B = px.shape[0]

@@ -62,7 +62,10 @@ template <int TPAD, int QW>
 struct AttCfg {
   static constexpr int QROWS = QW * 16;
   static constexpr int BUF_BYTES = ((2 * TPAD + QROWS) * ATT_LD * 2 + TPAD + 15) / 16 * 16;
-  static constexpr int SMEM_BYTES = 2 * BUF_BYTES;
+  // long sequences (SigLIP vision, 196 tokens: 76 KB per item) keep ONE buffer so that two CTAs fit on an SM;
+  // short ones double-buffer (the next item streams in while the current one is computed)
+  static constexpr int NBUF = (BUF_BYTES > 56 * 1024) ? 1 : 2;
+  static constexpr int SMEM_BYTES = NBUF * BUF_BYTES;
   static constexpr int QBLOCKS = (TPAD / 16 + QW - 1) / QW;
 };
 
@@ -129,13 +132,21 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
   int item = blockIdx.x;
   int buf = 0;
-  if (item < total) prefetch(item, 0);
-  cp_async_commit();
-  for (; item < total; item += gridDim.x) {
-    const int next = item + gridDim.x;
-    if (next < total) prefetch(next, buf ^ 1);
+  if (C::NBUF == 2) {
+    if (item < total) prefetch(item, 0);
     cp_async_commit();
-    cp_async_wait<1>();          // everything but the newest group (= the next item) has landed
+  }
+  for (; item < total; item += gridDim.x) {
+    if (C::NBUF == 2) {
+      const int next = item + gridDim.x;
+      if (next < total) prefetch(next, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();        // everything but the newest group (= the next item) has landed
+    } else {
+      prefetch(item, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     int b, h, z;
@@ -269,7 +280,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       }
     }
     __syncthreads();             // everyone is done with `buf` before the prefetch of the iteration after next refills it
-    buf ^= 1;
+    if (C::NBUF == 2) buf ^= 1;
   }
   cp_async_wait<0>();
 }

@@ -382,7 +382,7 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
   else if (T <= 64) r = launch_att<64, 4>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else if (T <= 80) r = launch_att<80, 5>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else if (T <= 128) r = launch_att<128, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
-  else if (T <= 208) r = launch_att<208, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
+  else if (T <= 208) r = launch_att<208, 4>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else if (T <= 256) r = launch_att<256, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len);
   else return fail(MMCM_EINVAL, "attention: sequence length %d > 256 is not supported", T);
   CKR(r);

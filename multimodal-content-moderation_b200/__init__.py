@@ -10,7 +10,8 @@ Importing this package never touches CUDA; the extension is loaded (and, if stal
 """
 from . import arch, build, lib, prepost, sharding, synthetic  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .pipeline import BatchedScorer  # noqa: F401
 from .modules import FocalWithLogitsLoss, MultiModalFusionClassifier, MultiTaskClassifier  # noqa: F401
 
-__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "arch", "build",
+__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "BatchedScorer", "arch", "build",
            "lib", "prepost", "sharding", "synthetic"]

@@ -807,6 +807,14 @@ static double chunk_cost(const TowerW& t, int T, int n, int sms) {
 }
 static int choose_chunk(const TowerW& t, int T, int B, int cap, int sms) {
   if (cap > B) cap = B;
+  // the search is ~1000 cost evaluations: remember the answer per (tower shape, T, B, cap)
+  static std::map<std::tuple<int, int, int, int, int, int>, int> memo;
+  const auto key = std::make_tuple(t.D, t.F, t.L, T, B, cap);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+  }
   int best = cap;
   double best_cost = 1e300;
   for (int c = cap; c >= 16 || c == cap; --c) {
@@ -815,6 +823,9 @@ static int choose_chunk(const TowerW& t, int T, int B, int cap, int sms) {
     const double cost = full * chunk_cost(t, T, c, sms) + chunk_cost(t, T, rem, sms);
     if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
   }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (memo.size() > 4096) memo.clear();
+  memo[key] = best;
   return best;
 }
 

@@ -1,0 +1,69 @@
+"""Batched scoring in the callers' place.
+
+The reference scores one sample per forward: `MultiModalClassifier.predict_batch` is a Python loop over `predict`
+(R/scripts/inference.py:256-270) and SageMaker's `predict_fn` loops over instances (R/sagemaker/inference.py:241-296).
+`BatchedScorer` takes the already tokenised ids and the already resized / cropped uint8 images of MANY requests and
+runs them as one batch: uint8 -> ToTensor/Normalize on the GPU (prepost.preprocess_u8), one forward, fused
+sigmoid / thresholds / any_harmful (prepost.postprocess).  Tokenisation, JPEG decode and PIL's antialiased resize stay
+on the CPU exactly as in the reference (R/src/data/dataset.py:106-165).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import prepost
+
+
+class BatchedScorer:
+    def __init__(self, model: torch.nn.Module, class_names: Sequence[str], thresholds: Sequence[float],
+                 image_mean: Sequence[float] = (0.48145466, 0.4578275, 0.40821073),
+                 image_std: Sequence[float] = (0.26862954, 0.26130258, 0.27577711), max_batch: int = 1024):
+        self.model = model.eval()
+        self.class_names = list(class_names)
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedScorer needs the model on a CUDA device: no CPU fallback")
+        self.thresholds = torch.tensor(list(thresholds), dtype=torch.float32, device=self.device)
+        if self.thresholds.numel() != len(self.class_names):
+            raise ValueError("one threshold per class is required")      # inference.py:118-121 pads/validates likewise
+        self.mean, self.std, self.max_batch = list(image_mean), list(image_std), int(max_batch)
+
+    @torch.no_grad()
+    def score(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, images_u8: Optional[torch.Tensor],
+              text_present: Optional[torch.Tensor] = None, image_present: Optional[torch.Tensor] = None
+              ) -> Dict[str, torch.Tensor]:
+        """input_ids / attention_mask [N,S] int64, images_u8 [N,H,W,3] uint8 (or None: no images at all).
+        Returns probs [N,C], labels [N,C] bool, any_harmful [N] bool -- the fields of inference.py:220-232."""
+        N = input_ids.shape[0]
+        dev = self.device
+        a = self.model._arch
+        tp = torch.ones(N, device=dev) if text_present is None else text_present.to(dev, torch.float32)
+        if images_u8 is None:                                            # inference.py:142-166: zero image, flag 0
+            ip = torch.zeros(N, device=dev)
+        else:
+            ip = torch.ones(N, device=dev) if image_present is None else image_present.to(dev, torch.float32)
+        outs: List[Dict[str, torch.Tensor]] = []
+        for s in range(0, N, self.max_batch):
+            e = min(s + self.max_batch, N)
+            if images_u8 is None:
+                px = torch.zeros(e - s, 3, a.image, a.image, device=dev)
+            else:
+                px = prepost.preprocess_u8(images_u8[s:e].to(dev, non_blocking=True), self.mean, self.std)
+            logits = self.model(input_ids=input_ids[s:e].to(dev, non_blocking=True),
+                                attention_mask=attention_mask[s:e].to(dev, non_blocking=True), pixel_values=px,
+                                text_present=tp[s:e], image_present=ip[s:e])["logits"]
+            outs.append(prepost.postprocess(logits, self.thresholds))
+        return {k: torch.cat([o[k] for o in outs], dim=0) for k in ("probs", "labels", "any_harmful")}
+
+    def as_records(self, result: Dict[str, torch.Tensor]) -> List[dict]:
+        """The per-request dictionaries `predict` returns (inference.py:220-234)."""
+        probs, labels, anyh = result["probs"].cpu(), result["labels"].cpu(), result["any_harmful"].cpu()
+        thr = self.thresholds.cpu()
+        recs = []
+        for i in range(probs.shape[0]):
+            preds = {n: {"label": bool(labels[i, j]), "probability": float(probs[i, j]), "threshold": float(thr[j])}
+                     for j, n in enumerate(self.class_names)}
+            recs.append({"predictions": preds, "any_harmful": bool(anyh[i])})
+        return recs

@@ -62,3 +62,38 @@ def test_u8_pipeline_feeds_the_forward():
     b_ref = dict(batch, pixel_values=orc.to_tensor_normalize(img, mean, std).cuda())
     b_u8 = dict(batch, pixel_values=prepost.preprocess_u8(img.cuda(), mean, std))
     assert torch.equal(m(**b_ref)["logits"], m(**b_u8)["logits"])
+
+
+def test_batched_scorer_equals_per_sample_reference_flow():
+    """One batched call == the reference's per-request loop (tokenised ids + uint8 crops in, records out)."""
+    import numpy as np
+    import mmcm_b200 as P
+    from conftest import build_case
+    from test_gpu_forward import _make_module
+    from mmcm_b200 import synthetic as syn
+    from oracle import prepost_oracle as orc
+    from oracle import scoring_oracle as so
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    N = 21
+    b = syn.make_inputs(a, N, seed=80)
+    img = torch.randint(0, 256, (N, 224, 224, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    names = ["racist", "sexist", "homophobe", "religion", "otherhate"]
+    thr = [0.2, 0.35, 0.5, 0.8, 0.95]
+    scorer = P.BatchedScorer(m, names, thr, max_batch=8)
+    res = scorer.score(b["input_ids"], b["attention_mask"], img)
+    recs = scorer.as_records(res)
+    assert len(recs) == N and set(recs[0]["predictions"]) == set(names)
+    # oracle: reference transform tail -> reference forward -> reference post-processing, on the CPU
+    mean, std = scorer.mean, scorer.std
+    batch = dict(b, pixel_values=orc.to_tensor_normalize(img, mean, std), image_present=torch.ones(N))
+    with torch.no_grad():
+        ref_logits = so.fusion_forward(sd, batch, "clip", a.patch, a.eos_id)
+    p_ref, l_ref, a_ref = orc.postprocess(ref_logits.numpy(), np.array(thr, dtype=np.float32))
+    probs = res["probs"].cpu().numpy()
+    assert np.abs(probs - p_ref).max() <= 0.25 * 0.05 * float(ref_logits.std())      # sigmoid-Lipschitz of the logit gate
+    far = np.abs(p_ref - np.array(thr)[None]) > 0.25 * 0.05 * float(ref_logits.std())
+    assert (res["labels"].cpu().numpy() == l_ref)[far].all()
+    # no image at all -> image_present = 0 path
+    res2 = scorer.score(b["input_ids"][:4], b["attention_mask"][:4], None)
+    assert res2["probs"].shape == (4, 5)

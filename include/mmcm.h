@@ -118,8 +118,8 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  * chunk size <= micro_batch whose GEMM tile counts fill whole waves of the 148 SMs; 0 = use micro_batch as is),
  * "varlen_text" (1 = default: the causal CLIP text tower keeps only the rows up to each sample's pooled EOS
  * position, packed back to back -- bit-identical logits, fewer rows; 0 = compute all S rows like the reference),
- * "attention_impl" (0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64),
- * mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 128; process-wide),
+ * "attention_impl" (0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64)
+ * and for 128 < T <= 256, mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 256; process-wide),
  * "tma_epilogue" (1 = TMA tile-store / reduce-add epilogue of the pair GEMM; process-wide),
  * "graph_max_batch" (forwards with B <= this are replayed as one CUDA graph from the third call of a shape on;
  * 0 = off = default: measured on B200 the 177-kernel chain of a B=1 forward is GPU-latency bound, 1.45 ms either way), "streams" (1 or 2: text/vision towers on separate streams), "pdl" (1 = launch every kernel with programmatic

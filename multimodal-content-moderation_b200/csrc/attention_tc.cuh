@@ -28,8 +28,19 @@ namespace mmcm {
 
 constexpr int ATC_THREADS = 192;
 constexpr int ATC_TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
-constexpr int ATC_SMEM_BYTES = 3 * ATC_TILE_BYTES + 1024;   // Q | K | V (+ 1 KB alignment slack); P overwrites Q | K
-constexpr int ATC_TMEM_COLS = 128;
+// KMAX = most keys a query row can see (= TMEM columns of S): 128 for everything up to 128 tokens (G samples per tile),
+// 256 for longer sequences (SigLIP vision, 196 tokens: one sample, ceil(T/128) row tiles that each see all keys).
+// smem: Q (16 KB) | K (KMAX rows) | [pad so that P = 128 x KMAX bf16 fits over Q|K|pad] | V (KMAX rows)
+template <int KMAX>
+struct AtcCfg {
+  static constexpr int K_BYTES = KMAX * 128;
+  static constexpr int P_BYTES = (KMAX / 64) * ATC_TILE_BYTES;
+  static constexpr int V_OFF = P_BYTES > ATC_TILE_BYTES + K_BYTES ? P_BYTES : ATC_TILE_BYTES + K_BYTES;
+  static constexpr int SMEM_BYTES = V_OFF + K_BYTES + 1024;   // + 1 KB alignment slack
+  static constexpr int TMEM_COLS = KMAX;
+  static constexpr int KW = KMAX / 32;                         // 32-key validity words / score chunks
+  static constexpr int CTAS_PER_SM = 512 / KMAX;               // TMEM (and smem: 49 KB / 97 KB) limit
+};
 
 // instruction descriptor: D=f32, A=B=bf16, A K-major, B K-major (b_mn = 0) or MN-major (b_mn = 1)
 __device__ __forceinline__ uint32_t atc_idesc(int M, int N, int b_mn) {
@@ -40,21 +51,25 @@ __device__ __forceinline__ uint32_t atc_idesc(int M, int N, int b_mn) {
 // fixed-length mode (seq_start == nullptr): sample b owns rows [b*T, (b+1)*T), box_rows = T, G samples per tile
 // packed mode: sample b owns rows [seq_start[b], +seq_len[b]), box_rows = 128, one sample per tile
 // key_valid: one byte per qkv row (fixed-length: [B, T] contiguous) or nullptr
+template <int KMAX>
 __global__ void __launch_bounds__(ATC_THREADS)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
-                    const uint8_t* __restrict__ key_valid, const int* __restrict__ seq_start,
-                    const int* __restrict__ seq_len, const int T_fixed, const int D, const int causal, const int B,
-                    const int heads, const int box_rows, long long* __restrict__ trace) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    __nv_bfloat16* __restrict__ out, const uint8_t* __restrict__ key_valid,
+                    const int* __restrict__ seq_start, const int* __restrict__ seq_len, const int T_fixed, const int D,
+                    const int causal, const int B, const int heads, const int q_box, const int kv_box,
+                    long long* __restrict__ trace) {
+  using C = AtcCfg<KMAX>;
   extern __shared__ uint8_t atc_smem_raw[];
   __shared__ __align__(8) uint64_t bar_full, bar_s, bar_p, bar_o, bar_free;
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem, sK = smem + ATC_TILE_BYTES, sV = smem + 2 * ATC_TILE_BYTES;
+  const uint32_t sQ = smem, sK = smem + ATC_TILE_BYTES, sV = smem + C::V_OFF;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_qkv);
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_kv);
     mbar_init(smem_u32(&bar_full), 1);
     mbar_init(smem_u32(&bar_s), 1);
     mbar_init(smem_u32(&bar_p), 128);
@@ -63,7 +78,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc_imm<ATC_TMEM_COLS>(smem_u32(&tmem_holder));
+  if (warp == 1) tmem_alloc_imm<C::TMEM_COLS>(smem_u32(&tmem_holder));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -72,45 +87,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
   pdl_wait();
 
   const bool packed = seq_start != nullptr;
+  const bool longseq = !packed && T_fixed > 128;             // one sample per tile, RT row tiles, all keys visible
   // slot = rows reserved per sample inside the tile (power of two >= T, at least one UMMA k-step)
-  const int slot_shift = packed ? 7 : (T_fixed <= 16 ? 4 : (T_fixed <= 32 ? 5 : (T_fixed <= 64 ? 6 : 7)));
+  const int slot_shift = (packed || longseq) ? 7 : (T_fixed <= 16 ? 4 : (T_fixed <= 32 ? 5 : (T_fixed <= 64 ? 6 : 7)));
   const int SLOT = 1 << slot_shift;
   const int G = 128 >> slot_shift;                            // samples per tile
+  const int RT = longseq ? (T_fixed + 127) >> 7 : 1;          // row tiles per sample
   const int groups = (B + G - 1) / G;
-  const int total = groups * heads;
+  const int total = groups * heads * RT;
 
   // V padding rows (slot rows >= T) are never written by TMA: zero the V tile once so that 0-probability x stale
   // shared memory cannot produce NaN.  (The Q | K tiles are rewritten with finite P values every tile.)
-  for (int i = threadIdx.x; i < 3 * ATC_TILE_BYTES / 16; i += ATC_THREADS) sts128(smem + i * 16, 0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < (C::V_OFF + C::K_BYTES) / 16; i += ATC_THREADS) sts128(smem + i * 16, 0u, 0u, 0u, 0u);
   fence_proxy_async();
   __syncthreads();
 
-  // tile -> head, first sample, samples in the tile, rows per sample
-  auto tile_info = [&](int item, int& h, int& b0, int& ns, int& Tcur) {
+  // tile -> head, row tile, first sample, samples in the tile, rows per sample
+  auto tile_info = [&](int item, int& h, int& rt, int& b0, int& ns, int& Tcur) {
     h = item % heads;
-    b0 = (item / heads) * G;
+    int r = item / heads;
+    rt = r % RT;
+    r /= RT;
+    b0 = r * G;
     ns = min(G, B - b0);
     Tcur = packed ? seq_len[b0] : T_fixed;
   };
   auto first_row = [&](int b) { return packed ? seq_start[b] : b * T_fixed; };
+  // keys of the tile, rounded to the UMMA N / K step
+  auto key_extent = [&](int ns, int Tcur) { return (((ns - 1) << slot_shift) + Tcur + 15) & ~15; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      int h, b0, ns, Tcur;
-      tile_info(item, h, b0, ns, Tcur);
+      int h, rt, b0, ns, Tcur;
+      tile_info(item, h, rt, b0, ns, Tcur);
       mbar_wait(smem_u32(&bar_free), ph ^ 1u);       // previous tile fully consumed (smem and TMEM)
       if (lane == 0) {
         const uint32_t full = smem_u32(&bar_full);
-        // box = 64 dh x box_rows (box_rows = T in fixed-length mode, 128 in packed mode): one box per sample slot
-        mbar_expect_tx(full, (uint32_t)(3 * ns * box_rows * 128));
+        // one Q box (64 dh x q_box rows) and one K / V box (64 dh x kv_box rows) per sample slot
+        mbar_expect_tx(full, (uint32_t)(ns * (q_box + 2 * kv_box) * 128));
         for (int g = 0; g < ns; ++g) {
           const int row = first_row(b0 + g);
           const uint32_t off = (uint32_t)(g << slot_shift) * 128u;
-          tma_load_2d(&tmap_qkv, full, sQ + off, h * ATT_DH, row);
-          tma_load_2d(&tmap_qkv, full, sK + off, D + h * ATT_DH, row);
-          tma_load_2d(&tmap_qkv, full, sV + off, 2 * D + h * ATT_DH, row);
+          tma_load_2d(&tmap_q, full, sQ + off, h * ATT_DH, row + rt * 128);
+          tma_load_2d(&tmap_kv, full, sK + off, D + h * ATT_DH, row);
+          tma_load_2d(&tmap_kv, full, sV + off, 2 * D + h * ATT_DH, row);
         }
       }
       __syncwarp();
@@ -120,9 +142,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     // ===================== MMA issuer =====================
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      int h, b0, ns, Tcur;
-      tile_info(item, h, b0, ns, Tcur);
-      const int nk = (((ns - 1) << slot_shift) + Tcur + 15) & ~15;   // last live key row, rounded to the UMMA N / K step
+      int h, rt, b0, ns, Tcur;
+      tile_info(item, h, rt, b0, ns, Tcur);
+      const int nk = key_extent(ns, Tcur);
       mbar_wait(smem_u32(&bar_full), ph);
       tc_fence_after();
       if (lane == 0) {
@@ -155,23 +177,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     const float L2E = 1.4426950408889634f;
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      int h, b0, ns, Tcur;
-      tile_info(item, h, b0, ns, Tcur);
+      int h, rt, b0, ns, Tcur;
+      tile_info(item, h, rt, b0, ns, Tcur);
       // keys this row may attend: its own sample's slot, cut at the diagonal when causal
-      const int g = r >> slot_shift, q = r & (SLOT - 1);
+      const int g = r >> slot_shift;
+      const int q = (r & (SLOT - 1)) + rt * 128;                     // position of this row inside its sample
       const bool row_ok = g < ns && q < Tcur;
       const int lo = g << slot_shift;
       const int hi = row_ok ? lo + (causal ? q + 1 : Tcur) : lo;     // empty range for padding rows
       const int grow = row_ok ? first_row(b0 + g) + q : 0;           // global qkv / out row of this thread
-      const int nk = (((ns - 1) << slot_shift) + Tcur + 15) & ~15;
+      const int nk = key_extent(ns, Tcur);
       const int nchunks = (nk + 31) >> 5;                            // 32-column chunks covering the MMA's K extent
-      uint32_t kv[4];
+      uint32_t kv[C::KW];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < C::KW; ++w) {
         const int c = w * 32 + lane;
         const int cg = c >> slot_shift, ck = c & (SLOT - 1);
-        bool ok = cg < ns && ck < Tcur;
-        if (ok && key_valid) ok = key_valid[(size_t)first_row(b0 + cg) + ck] != 0;
+        bool ok = longseq ? c < Tcur : (cg < ns && ck < Tcur);
+        if (ok && key_valid) ok = key_valid[(size_t)first_row(b0 + (longseq ? 0 : cg)) + (longseq ? c : ck)] != 0;
         kv[w] = __ballot_sync(0xffffffffu, ok);
       }
 
@@ -303,7 +326,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_imm<ATC_TMEM_COLS>(tmem);
+    tmem_dealloc_imm<C::TMEM_COLS>(tmem);
   }
 }
 

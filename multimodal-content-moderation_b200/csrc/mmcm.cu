@@ -336,34 +336,41 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
 
 static long long* g_gemm_trace = nullptr;   // dev tool, see mmcm_debug_set_gemm_trace
 // 0 = auto: tcgen05 kernel when at least two samples share a 128-row tile (T <= 64: measured 80 vs 87 us for the
-// 50-token vision tower), mma.sync kernel otherwise (77-token text: 90 vs 98 us); 1 = always mma.sync; 2 = tcgen05
-// whenever T <= 128
+// 50-token vision tower) and for 128 < T <= 256 (SigLIP vision), mma.sync kernel otherwise (77-token text: 90 vs
+// 98 us); 1 = always mma.sync; 2 = tcgen05 whenever T <= 256
 static int g_attention_impl = 0;
 
+template <int KMAX>
 static int launch_attention_tc(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
                                cudaStream_t st, const int* seq_start, const int* seq_len) {
+  using C = AtcCfg<KMAX>;
   CKR(ensure_driver());
+  auto kern = attention_tc_kernel<KMAX>;
   static AttrOnce once;
   if (once.need()) {
-    CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
-  // 49 KB of shared memory and 128 of the SM's 512 TMEM columns per CTA -> 4 resident CTAs per SM.  (The occupancy
-  // calculator answers 1 for a kernel that allocates TMEM; the hardware does co-schedule them: 247 -> 142 -> 98 us
-  // for 1 / 2 / 4 CTAs per SM, tools/attn_trace.py.)
-  int ctas_per_sm = 4;
+  // KMAX = 128: 49 KB of shared memory and 128 of the SM's 512 TMEM columns per CTA -> 4 resident CTAs per SM
+  // (KMAX = 256: 97 KB, 256 columns -> 2).  The occupancy calculator answers 1 for a kernel that allocates TMEM; the
+  // hardware does co-schedule them: 247 -> 142 -> 98 us for 1 / 2 / 4 CTAs per SM (tools/attn_trace.py).
+  int ctas_per_sm = C::CTAS_PER_SM;
   if (getenv("MMCM_ATC_CTAS")) ctas_per_sm = atoi(getenv("MMCM_ATC_CTAS"));
   const int D = heads * ATT_DH;
-  const int box_rows = seq_start ? 128 : T;          // one TMA box per sample slot
-  CUtensorMap tq;
-  CKR(get_tmap(&tq, qkv, (int64_t)B * T, 3 * D, box_rows, false));
-  const int slot = seq_start ? 128 : (T <= 16 ? 16 : (T <= 32 ? 32 : (T <= 64 ? 64 : 128)));
+  const bool longseq = !seq_start && T > 128;
+  const int q_box = (seq_start || longseq) ? 128 : T;     // one TMA box per sample slot
+  const int kv_box = seq_start ? 128 : T;
+  CUtensorMap tq, tkv;
+  CKR(get_tmap(&tq, qkv, (int64_t)B * T, 3 * D, q_box, false));
+  CKR(get_tmap(&tkv, qkv, (int64_t)B * T, 3 * D, kv_box, false));
+  const int slot = (seq_start || longseq) ? 128 : (T <= 16 ? 16 : (T <= 32 ? 32 : (T <= 64 ? 64 : 128)));
   const int G = 128 / slot;
-  const int total = ((B + G - 1) / G) * heads;
+  const int RT = longseq ? (T + 127) / 128 : 1;
+  const int total = ((B + G - 1) / G) * heads * RT;
   int grid = g_num_sms * ctas_per_sm;
   if (grid > total) grid = total;
-  CK(launch_k(attention_tc_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, out, kvalid, seq_start, seq_len, T, D,
-              causal, B, heads, box_rows, g_gemm_trace));
+  CK(launch_k(kern, dim3(grid), dim3(ATC_THREADS), C::SMEM_BYTES, st, tq, tkv, out, kvalid, seq_start, seq_len, T, D, causal, B,
+              heads, q_box, kv_box, g_gemm_trace));
   return MMCM_OK;
 }
 
@@ -371,8 +378,11 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
                             cudaStream_t st, LaunchStats* stats, const int* seq_start = nullptr,
                             const int* seq_len = nullptr) {
   if (B <= 0) return MMCM_OK;
-  if ((g_attention_impl == 2 && T <= 128) || (g_attention_impl == 0 && T <= 64 && !seq_start)) {
-    CKR(launch_attention_tc(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
+  const bool tc128 = T <= 128 && (g_attention_impl == 2 || (g_attention_impl == 0 && T <= 64 && !seq_start));
+  const bool tc256 = T > 128 && T <= 256 && !seq_start && g_attention_impl != 1;
+  if (tc128 || tc256) {
+    if (tc128) CKR(launch_attention_tc<128>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
+    else CKR(launch_attention_tc<256>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
     if (stats) stats->launches++;
     return MMCM_OK;
   }

@@ -44,6 +44,23 @@ def _peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner on the process's stdout (fd 1) at the first collective; the contract is ONE JSON
+    line on stdout, so fd 1 points at stderr until the timed work is over."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -194,11 +211,11 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the scoring path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else None   # pinned buffers next to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
 
     if kind == "fusion":
         m = P.MultiModalFusionClassifier(enc, num_labels=5, **kw)
@@ -231,9 +248,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = step()
-    sync_all()
+    with _StdoutToStderr():
+        for _ in range(args.warmup):
+            out = step()
+        sync_all()
     launches_per_step = eng.last_launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -339,6 +357,7 @@ def main():
                 "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB/step/GPU vs 126 MB)",
                            "micro_batch": args.micro_batch or "library default", "streams": args.streams, "pdl": args.pdl,
+                           "numa_node_rank0": numa,
                            "varlen_text": args.varlen,
                            "algorithmic_gflop_per_sample": flops["total"] / 1e9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,

@@ -13,6 +13,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards
+    (first touch) and the H2D copies of `mmcm_forward_host` stay on the GPU's side of the machine.  One process per
+    GPU; a no-op (returns None) when the topology files are not readable."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) of rank `rank`: the first n % world ranks get one extra sample."""
     if world <= 0 or not (0 <= rank < world):

@@ -32,8 +32,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the pair leader's copy of `bar`
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+// arrive on the pair leader's copy of `bar`.  RELAXED: the only thing the waiter (the MMA warp) does afterwards is
+// overwrite TMEM, whose reads by this thread are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; no
+// generic-proxy memory is handed over.  The default .release.cluster arrive cost ~2.6 k cycles per tile here
+// (tools/gemm_trace.py: acc-ready -> epilogue-done 7.5 k cycles although the two chunks took 4.9 k).
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(

@@ -169,6 +169,7 @@ def main():
                          "one of the S rows the reference computes, the packed number is reported under `extras`")
     ap.add_argument("--pairs-text", type=int, default=0, help="CTA pairs the text-tower GEMMs may occupy (0 = all 74)")
     ap.add_argument("--pairs-vision", type=int, default=0)
+    ap.add_argument("--attention-impl", type=int, default=0, help="0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -230,6 +231,7 @@ def main():
     m.set_option("varlen_text", args.varlen)
     m.set_option("pairs_text", args.pairs_text)
     m.set_option("pairs_vision", args.pairs_vision)
+    m.set_option("attention_impl", args.attention_impl)
     eng = m._ensure_engine(local_rank)
 
     B = args.batch

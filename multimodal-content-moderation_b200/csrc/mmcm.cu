@@ -337,7 +337,8 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
 static long long* g_gemm_trace = nullptr;   // dev tool, see mmcm_debug_set_gemm_trace
 // 0 = auto: tcgen05 kernel when at least two samples share a 128-row tile (T <= 64: measured 80 vs 87 us for the
 // 50-token vision tower) and for 128 < T <= 256 (SigLIP vision), mma.sync kernel otherwise (77-token text: 90 vs
-// 98 us); 1 = always mma.sync; 2 = tcgen05 whenever T <= 256
+// 98 us; packed text stays on it too although tcgen05 would be 2 % faster end to end, so that packed and dense text
+// run the SAME attention kernel and stay bit-identical); 1 = always mma.sync; 2 = tcgen05 whenever T <= 256
 static int g_attention_impl = 0;
 
 template <int KMAX>

@@ -89,3 +89,16 @@ def test_create_rejects_bad_configs():
         P.Engine(A.SIGLIP2_B16, A.HEAD_MTL, 5)                               # MTL + siglip: reference asserts too
     with pytest.raises(ValueError):
         P.Engine(A.CLIP_B32, A.HEAD_FUSION, 5, device=99)
+
+
+def test_empty_batch_is_a_no_op():
+    from mmcm_b200 import arch as A, synthetic as syn
+    eng = _engine()
+    a = A.CLIP_B32
+    eng.load_state_dict(syn.make_state_dict(A.fusion_spec(a, 5, 512), a, seed=0))
+    ids = torch.zeros(0, 77, dtype=torch.long, device="cuda")
+    px = torch.zeros(0, 3, 224, 224, device="cuda")
+    f = torch.zeros(0, device="cuda")
+    y = eng.forward(ids, ids, px, f, f)
+    assert y.shape == (0, 5)
+    eng.close()

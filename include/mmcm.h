@@ -113,18 +113,26 @@ MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
  * mmcm_set_option(h, "time_gemms", 1); also returns the FLOPs they EXECUTED (2*M*N*K with the live row count of
  * packed text chunks). Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
-/* Options: "time_gemms" (0/1), "gemm_impl" (0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel),
- * "micro_batch" (upper bound on the samples per internal pass of a tower), "auto_chunk" (1 = pick, per tower, the
- * chunk size <= micro_batch whose GEMM tile counts fill whole waves of the 148 SMs; 0 = use micro_batch as is),
- * "varlen_text" (1 = default: the causal CLIP text tower keeps only the rows up to each sample's pooled EOS
- * position, packed back to back -- bit-identical logits, fewer rows; 0 = compute all S rows like the reference),
- * "attention_impl" (0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64)
- * and for 128 < T <= 256, mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 256; process-wide),
- * "tma_epilogue" (1 = TMA tile-store / reduce-add epilogue of the pair GEMM; process-wide),
- * "graph_max_batch" (forwards with B <= this are replayed as one CUDA graph from the third call of a shape on;
- * 0 = off = default: measured on B200 the 177-kernel chain of a B=1 forward is GPU-latency bound, 1.45 ms either way), "streams" (1 or 2: text/vision towers on separate streams), "pdl" (1 = launch every kernel with programmatic
- * stream serialization so that prologues overlap the previous kernel's tail; process-wide), "debug_feats" (0/1: keep the projected
- * features of the fusion head for mmcm_get_stage "text_feat"/"vision_feat"). */
+/* Options (name -> meaning; * = process-wide rather than per handle):
+ *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)
+ *   "micro_batch"      upper bound on the samples per internal pass of a tower (default 1024)
+ *   "auto_chunk"       1 = pick, per tower, the chunk <= micro_batch whose GEMM tile counts fill whole rounds of the
+ *                      74 CTA pairs; 0 = use micro_batch as is
+ *   "varlen_text"      1 = default: the causal CLIP text tower keeps only the rows up to each sample's pooled EOS
+ *                      position, packed back to back -- bit-identical logits, fewer rows; 0 = all S rows like the reference
+ *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
+ *   "tma_epilogue" *   1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
+ *   "attention_impl" * 0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
+ *                      for 128 < T <= 256, mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 256
+ *   "pdl" *            1 = every kernel is launched with programmatic stream serialization (prologues overlap the
+ *                      previous kernel's tail)
+ *   "graph_max_batch"  forwards with B <= this are replayed as one CUDA graph from the third call of a shape on
+ *                      (default 0 = off: a B=1 forward is bound by its 177-kernel dependency chain on the GPU, 1.45 ms
+ *                      with or without replay)
+ *   "pairs_text", "pairs_vision"  > 0: cap the CTA pairs the tower's GEMMs may occupy (SM partitioning experiment;
+ *                      measured slower than letting every GEMM use all 74 pairs)
+ *   "time_gemms"       1 = record CUDA events around every GEMM launch (see mmcm_gemm_time)
+ *   "debug_feats"      1 = keep the projected features of the fusion head for mmcm_get_stage "text_feat"/"vision_feat" */
 MMCM_API int mmcm_set_option(mmcm_handle h, const char* name, int64_t value);
 MMCM_API const char* mmcm_last_error(void);
 MMCM_API const char* mmcm_version(void);

@@ -120,27 +120,31 @@ class _B200ScoringModule(nn.Module):
         return probs
 
 
+def focal_with_logits(logits: torch.Tensor, targets: torch.Tensor, alpha: Optional[torch.Tensor] = None,
+                      gamma: float = 1.5, reduction: str = "mean") -> torch.Tensor:
+    """Focal BCE on logits, the formula of R/src/models/fusion.py:39-52: ce * (1 - p_t)^gamma [* alpha_t] with
+    p_t = p t + (1 - p)(1 - t) written as a lerp between the negative- and positive-class probabilities."""
+    p = torch.sigmoid(logits)
+    p_t = torch.lerp(1.0 - p, p, targets)
+    per_elem = F.binary_cross_entropy_with_logits(logits, targets, reduction="none") * (1.0 - p_t).pow(gamma)
+    if alpha is not None:
+        per_elem = per_elem * torch.lerp(1.0 - alpha, alpha, targets)
+    if reduction == "none":
+        return per_elem
+    return per_elem.mean() if reduction == "mean" else per_elem.sum()
+
+
 class FocalWithLogitsLoss(nn.Module):
-    """R/src/models/fusion.py:16-52 (evaluation-time loss reporting only)."""
+    """Module form of `focal_with_logits` (same constructor as the reference's class, fusion.py:16-37); only used to
+    report an evaluation-time loss when `labels` are passed."""
 
     def __init__(self, alpha: Optional[torch.Tensor] = None, gamma: float = 1.5, reduction: str = "mean"):
         super().__init__()
-        self.register_buffer("alpha", alpha if alpha is not None else None)
-        self.gamma = gamma
-        self.reduction = reduction
+        self.register_buffer("alpha", alpha)
+        self.gamma, self.reduction = gamma, reduction
 
     def forward(self, logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        prob = torch.sigmoid(logits)
-        ce = F.binary_cross_entropy_with_logits(logits, targets, reduction="none")
-        p_t = prob * targets + (1 - prob) * (1 - targets)
-        loss = ce * ((1 - p_t) ** self.gamma)
-        if self.alpha is not None:
-            loss = loss * (self.alpha * targets + (1 - self.alpha) * (1 - targets))
-        if self.reduction == "mean":
-            return loss.mean()
-        if self.reduction == "sum":
-            return loss.sum()
-        return loss
+        return focal_with_logits(logits, targets, self.alpha, self.gamma, self.reduction)
 
 
 class MultiModalFusionClassifier(_B200ScoringModule):

@@ -85,3 +85,20 @@ def test_synthetic_inputs_follow_survey_spec():
         assert (ids[r, lens[r] - 1:] == 49407).all() and (ids[r, 1:lens[r] - 1] < 49406).all()
     s = syn.make_inputs(A.SIGLIP2_B16, 16, seed=1)
     assert s["input_ids"].shape == (16, 64)
+
+
+def test_focal_loss_formula():
+    """Evaluation-time focal loss (fusion.py:39-52): ce * (1 - p_t)^gamma * alpha_t, hard and soft targets."""
+    import torch.nn.functional as F
+    from mmcm_b200.modules import FocalWithLogitsLoss
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(32, 5, generator=g) * 3
+    alpha = torch.tensor([0.25, 0.5, 0.75, 0.3, 0.6])
+    for t in ((torch.rand(32, 5, generator=g) < 0.3).float(), torch.rand(32, 5, generator=g)):
+        p = torch.sigmoid(z)
+        ce = F.binary_cross_entropy_with_logits(z, t, reduction="none")
+        ref = ce * (1 - (p * t + (1 - p) * (1 - t))) ** 2.0 * (alpha * t + (1 - alpha) * (1 - t))
+        assert torch.allclose(FocalWithLogitsLoss(alpha, 2.0, "none")(z, t), ref, atol=1e-6)
+        assert torch.allclose(FocalWithLogitsLoss(alpha, 2.0, "mean")(z, t), ref.mean(), atol=1e-6)
+        assert torch.allclose(FocalWithLogitsLoss(None, 2.0, "sum")(z, t),
+                              (ce * (1 - (p * t + (1 - p) * (1 - t))) ** 2.0).sum(), atol=1e-4)

@@ -285,3 +285,24 @@ def test_config5_shard_size_properties():
     sl = slice(1000, 1064)
     ys = m(**{k: v[sl].contiguous() for k, v in batch.items()})["logits"]
     assert torch.equal(ys, y[sl])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_second_device_while_current_device_is_zero():
+    """One process, two handles on two devices (the reference's `.to(device)` with device = cuda:1)."""
+    import mmcm_b200 as P
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    batch = syn.make_inputs(a, 16, seed=90, edge_rows=True)
+    m0 = _make_module(kind, a, kw, sd)
+    y0 = m0(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
+    m1 = P.MultiModalFusionClassifier("openai/clip-vit-base-patch32", num_labels=5, **kw)
+    m1.load_state_dict(sd)
+    m1 = m1.to("cuda:1").eval()
+    torch.cuda.set_device(0)                                   # current device stays 0
+    y1 = m1(**{k: v.to("cuda:1") for k, v in batch.items()})["logits"]
+    assert y1.device.index == 1
+    assert torch.equal(y1.cpu(), y0)
+    assert torch.equal(m0(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu(), y0)
+    with pytest.raises(RuntimeError, match="different devices"):
+        m1(**{k: v.to("cuda:0") for k, v in batch.items()})

@@ -167,6 +167,10 @@ def main():
     ap.add_argument("--varlen", type=int, default=0,
                     help="1 = packed variable-length CLIP text (exact, fewer rows); the headline keeps 0 = every "
                          "one of the S rows the reference computes, the packed number is reported under `extras`")
+    ap.add_argument("--pooled-last", type=int, default=1,
+                    help="1 = library default: after the last layer's attention only the pooled row of each sample "
+                         "runs out_proj / MLP / final LN (row-wise ops, bit-identical logits); 0 = all rows. The "
+                         "other setting is reported under `extras`")
     ap.add_argument("--pairs-text", type=int, default=0, help="CTA pairs the text-tower GEMMs may occupy (0 = all 74)")
     ap.add_argument("--pairs-vision", type=int, default=0)
     ap.add_argument("--attention-impl", type=int, default=0, help="0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256")
@@ -229,6 +233,7 @@ def main():
     m.set_option("streams", args.streams)
     m.set_option("pdl", args.pdl)
     m.set_option("varlen_text", args.varlen)
+    m.set_option("pooled_last_layer", args.pooled_last)
     m.set_option("pairs_text", args.pairs_text)
     m.set_option("pairs_vision", args.pairs_vision)
     m.set_option("attention_impl", args.attention_impl)
@@ -272,10 +277,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ------------------------------------------------------------------ extras: the same steps with packed CLIP text
-    extras = None
-    if a.backend == 0 and not args.no_e2e:
-        m.set_option("varlen_text", 1 - args.varlen)
+    # ------------------------------------------------------------------ extras: the same steps with one option flipped
+    def timed_variant(option, setting, restore):
+        m.set_option(option, setting)
         for _ in range(3):
             step()
         sync_all()
@@ -287,11 +291,21 @@ def main():
         xms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(xms, op=dist.ReduceOp.MAX)
-        m.set_option("varlen_text", args.varlen)
-        extras = {f"value_varlen_text_{1 - args.varlen}": world * B * args.steps / (xms.item() * 1e-3),
-                  "note": "varlen_text=1 packs the causal CLIP text tower up to each sample's EOS row (bit-identical "
-                          "logits, ~48 % fewer text rows on len~U{3..77}); the headline `value` uses varlen_text="
-                          f"{args.varlen}"}
+        m.set_option(option, restore)
+        return world * B * args.steps / (xms.item() * 1e-3)
+
+    extras = None
+    if not args.no_e2e:
+        extras = {f"value_pooled_last_layer_{1 - args.pooled_last}":
+                      timed_variant("pooled_last_layer", 1 - args.pooled_last, args.pooled_last),
+                  "note_pooled_last_layer": "1 = only the pooled row of each sample (CLS / EOS / last token) runs the last "
+                                            "layer's out_proj, LN2, MLP and final LN: those ops are row-wise, logits are "
+                                            f"bit-identical; the headline `value` uses {args.pooled_last}"}
+        if a.backend == 0:
+            extras[f"value_varlen_text_{1 - args.varlen}"] = timed_variant("varlen_text", 1 - args.varlen, args.varlen)
+            extras["note"] = ("varlen_text=1 packs the causal CLIP text tower up to each sample's EOS row (bit-identical "
+                              "logits, ~48 % fewer text rows on len~U{3..77}); the headline `value` uses varlen_text="
+                              f"{args.varlen}")
 
     # ------------------------------------------------------------------ e2e: host buffers through mmcm_forward_host
     e2e = None
@@ -360,7 +374,7 @@ def main():
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB/step/GPU vs 126 MB)",
                            "micro_batch": args.micro_batch or "library default", "streams": args.streams, "pdl": args.pdl,
                            "numa_node_rank0": numa,
-                           "varlen_text": args.varlen,
+                           "varlen_text": args.varlen, "pooled_last_layer": args.pooled_last,
                            "algorithmic_gflop_per_sample": flops["total"] / 1e9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu, "parity": parity, "extras": extras}

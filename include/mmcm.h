@@ -104,7 +104,8 @@ MMCM_API int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const in
 /* Introspection ------------------------------------------------------------------------------ */
 /* Copies an intermediate of the LAST forward into dst (device fp32).  Names: "text_pooled",
  * "vision_pooled" (tower pooler_output, fp32 [B,D]), "text_hidden", "vision_hidden" (residual stream
- * after the last layer, fp32 [B*T,D]).  *numel_out receives the element count. */
+ * fp32 [B*T,D]: after the last layer with option "pooled_last_layer" = 0; with the default 1 the last layer only
+ * advances the pooled rows, so these hold the last layer's INPUT).  *numel_out receives the element count. */
 MMCM_API int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity, int64_t* numel_out,
                    void* stream);
 /* Number of kernels this library launched during the last mmcm_forward on this handle. */
@@ -120,6 +121,11 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  *                      74 CTA pairs; 0 = use micro_batch as is
  *   "varlen_text"      1 = default: the causal CLIP text tower keeps only the rows up to each sample's pooled EOS
  *                      position, packed back to back -- bit-identical logits, fewer rows; 0 = all S rows like the reference
+ *   "pooled_last_layer" 1 = default: after the last layer's attention only the one row per sample that is pooled
+ *                      (CLIP vision CLS, CLIP text EOS, SigLIP text last token) goes through out_proj / LN2 / MLP /
+ *                      final LN -- those ops are row-wise, so the logits are bit-identical and 6 % of the GEMM work
+ *                      is skipped; 0 = all rows like the reference.  (SigLIP vision always runs all rows: its MAP
+ *                      head reads every token.)
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue" *   1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl" * 0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and

@@ -447,6 +447,9 @@ struct Arena {  // activations of one tower for one micro-batch
   bf16* ff = nullptr;    // [rows, F]
   int* pool_row = nullptr;
   int *seq_start = nullptr, *seq_len = nullptr, *rows_dev = nullptr;   // packed variable-length text
+  // last layer on the pooled rows only (one row per sample): residual, attention output, LN2 output, MLP hidden
+  float* xp = nullptr;
+  bf16 *attp = nullptr, *hp = nullptr, *ffp = nullptr;
   int64_t rows = 0;
 };
 
@@ -498,6 +501,7 @@ struct mmcm_handle_s {
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
   int opt_graph_max_batch = 0;   // off by default: small batches are bound by the GPU-side kernel chain, not the host
   int opt_pairs_text = 0, opt_pairs_vis = 0;   // > 0: CTA pairs the text / vision GEMMs may occupy (two-stream SM split)
+  int opt_pooled_last = 1;   // last layer: out_proj / MLP / final LN only for the one row per sample that is pooled (exact)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   int last_chunk_text = 0, last_chunk_vis = 0;
@@ -735,6 +739,7 @@ static int setup_weights(Eng* e) {
 static void free_arena(Eng* e, Arena& a) {
   dfree(e, a.x); dfree(e, a.h); dfree(e, a.qkv); dfree(e, a.att); dfree(e, a.ff); dfree(e, a.pool_row);
   dfree(e, a.seq_start); dfree(e, a.seq_len); dfree(e, a.rows_dev);
+  dfree(e, a.xp); dfree(e, a.attp); dfree(e, a.hp); dfree(e, a.ffp);
   a = Arena();
 }
 static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) {
@@ -748,6 +753,14 @@ static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) 
   CKR(dalloc(e, &a.seq_start, mb));
   CKR(dalloc(e, &a.seq_len, mb));
   CKR(dalloc(e, &a.rows_dev, 256));   // one live-row counter per packed chunk of a forward (accounting reads them back)
+  CKR(dalloc(e, &a.xp, (int64_t)mb * t.D));
+  CKR(dalloc(e, &a.attp, (int64_t)mb * t.D));
+  CKR(dalloc(e, &a.hp, (int64_t)mb * t.D));
+  CKR(dalloc(e, &a.ffp, (int64_t)mb * t.F));
+  CK(cudaMemset(a.xp, 0, (int64_t)mb * t.D * sizeof(float)));
+  CK(cudaMemset(a.attp, 0, (int64_t)mb * t.D * sizeof(bf16)));
+  CK(cudaMemset(a.hp, 0, (int64_t)mb * t.D * sizeof(bf16)));
+  CK(cudaMemset(a.ffp, 0, (int64_t)mb * t.F * sizeof(bf16)));
   // TMA tiles of partially filled chunks also cover rows nobody wrote in this forward: they must hold finite numbers
   // (a masked probability of 0 times a stale NaN in V would still be NaN)
   CK(cudaMemset(a.x, 0, rows * t.D * sizeof(float)));
@@ -855,8 +868,11 @@ static int ensure_batch(Eng* e, int64_t B) {
 }
 
 // ------------------------------------------------------------------------------------------------ towers
+// `pooled_last`: a.pool_row holds the one row per sample the caller reads after the last layer; the last layer then
+// runs out_proj / LN2 / MLP on those B rows only and leaves their residual in a.xp [B, D] (a.x keeps the last layer's
+// INPUT).  Row-wise ops on gathered rows give the same bits as on the full matrix.
 static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T, const uint8_t* kvalid, int causal,
-                      cudaStream_t st, const int* packed_rows = nullptr) {
+                      cudaStream_t st, const int* packed_rows = nullptr, bool pooled_last = false) {
   LaunchStats* S = &e->stats;
   const int D = t.D, F = t.F, impl = e->opt_gemm_impl;
   const bool packed = packed_rows != nullptr;
@@ -873,6 +889,23 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
     CKR(launch_gemm(a.h, w.wqkv, rows, 3 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
     // att = softmax(q k^T + mask) v                            HF clip :321-332
     CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S, sstart, slen));
+    if (pooled_last && i == t.L - 1) {
+      CK(launch_k(gather_pool_rows_kernel, dim3((B + 7) / 8), dim3(256), 0, st, (const bf16*)a.att, (const float*)a.x,
+                  (const int*)a.pool_row, B, D, a.attp, a.xp));
+      CK(cudaGetLastError());
+      S->launches++;
+      ep = EpiParams{};
+      ep.bias = w.bo; ep.out = a.xp; ep.resid = a.xp; ep.ldo = D;
+      CKR(launch_gemm(a.attp, w.wo, B, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
+      CKR(launch_layernorm(a.xp, w.ln2g, w.ln2b, t.eps, B, D, nullptr, a.hp, nullptr, st, S));
+      ep = EpiParams{};
+      ep.bias = w.b1; ep.out = a.ffp; ep.ldo = F; ep.act = t.act;
+      CKR(launch_gemm(a.hp, w.w1, B, F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
+      ep = EpiParams{};
+      ep.bias = w.b2; ep.out = a.xp; ep.resid = a.xp; ep.ldo = D;
+      CKR(launch_gemm(a.ffp, w.w2, B, D, F, EPI_BIAS_RESID_F32, ep, impl, st, S));
+      break;
+    }
     // x = x + att @ Wo^T + bo                                  HF clip :334, :379
     ep = EpiParams{};
     ep.bias = w.bo; ep.out = a.x; ep.resid = a.x; ep.ldo = D; ep.m_dev = rdev;
@@ -920,11 +953,13 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
     e->stats.launches++;
   }
   g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_text : 0;
-  const int rl = run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr);
+  const bool pl = e->opt_pooled_last && S > 1;
+  const int rl = run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr, pl);
   g_pair_limit = 0;
   CKR(rl);
   // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
-  CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
+  if (pl) CKR(launch_layernorm(a.xp, e->tfin_g, e->tfin_b, t.eps, n, t.D, nullptr, nullptr, pooled, st, &e->stats));
+  else CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
   e->last_text_rows = rows;
   return MMCM_OK;
 }
@@ -954,15 +989,19 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
     S->launches++;
     CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
   }
-  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_vis : 0;
-  const int rl = run_layers(e, t, a, rows, n, T, nullptr, 0, st);
-  g_pair_limit = 0;
-  CKR(rl);
-  if (clip) {
+  if (clip) {   // pooled row = CLS (row 0 of each sample)
     CK(launch_k(fill_pool_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a.pool_row, n, T, 0));
     CK(cudaGetLastError());
     S->launches++;
-    CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S));
+  }
+  const bool pl = clip && e->opt_pooled_last;   // the SigLIP MAP head reads every token of the last layer
+  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_vis : 0;
+  const int rl = run_layers(e, t, a, rows, n, T, nullptr, 0, st, nullptr, pl);
+  g_pair_limit = 0;
+  CKR(rl);
+  if (clip) {
+    if (pl) CKR(launch_layernorm(a.xp, e->post_g, e->post_b, t.eps, n, D, nullptr, nullptr, pooled, st, S));
+    else CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S));
   } else {
     // post_layernorm over all tokens, then the MAP head   HF siglip :617-649
     const int impl = e->opt_gemm_impl;
@@ -1446,6 +1485,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
+  else if (n == "pooled_last_layer") h->opt_pooled_last = value != 0;
   else if (n == "pairs_text" || n == "pairs_vision") {
     if (value < 0 || value > 74) return fail(MMCM_EINVAL, "%s must be in [0, 74]", name);
     (n == "pairs_text" ? h->opt_pairs_text : h->opt_pairs_vis) = (int)value;
@@ -1455,6 +1495,9 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     h->opt_graph_max_batch = (int)value;
   }
   else return fail(MMCM_EINVAL, "unknown option '%s'", name);
+  // captured graphs bake the launch sequence of the options they were recorded under
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
   return MMCM_OK;
 }
 

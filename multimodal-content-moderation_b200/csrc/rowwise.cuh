@@ -275,6 +275,25 @@ __global__ void fill_pool_rows_kernel(int* __restrict__ pool_row, const int B, c
   if (b < B) pool_row[b] = b * T + t0;
 }
 
+// Last encoder layer, pooled rows only: only row pool_row[b] of each sample is read after the last layer (CLS / EOS /
+// last token, HF clip :575-584, :688-689), and everything after the attention core is row-wise (out_proj, residual,
+// LN2, MLP, final LN).  Gather those rows of the attention output (bf16) and of the residual stream (fp32) into
+// dense [B, D] buffers; the remaining GEMMs of the layer then run with M = B instead of M = B*T.  One warp per row.
+__global__ void gather_pool_rows_kernel(const __nv_bfloat16* __restrict__ att, const float* __restrict__ x,
+                                        const int* __restrict__ pool_row, const int B, const int D,
+                                        __nv_bfloat16* __restrict__ att_p, float* __restrict__ x_p) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const size_t src = (size_t)pool_row[b] * D, dst = (size_t)b * D;
+  for (int c = lane * 8; c < D; c += 256)
+    *reinterpret_cast<uint4*>(att_p + dst + c) = *reinterpret_cast<const uint4*>(att + src + c);
+  for (int c = lane * 4; c < D; c += 128)
+    *reinterpret_cast<float4*>(x_p + dst + c) = *reinterpret_cast<const float4*>(x + src + c);
+}
+
 // fp32 -> bf16 (weights repack; `scale` folds dh^-1/2 into the Q projection -- exact, 1/8 is a power of two)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, const size_t n,
                                  const float scale) {

@@ -306,3 +306,29 @@ def test_model_on_second_device_while_current_device_is_zero():
     assert torch.equal(m0(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu(), y0)
     with pytest.raises(RuntimeError, match="different devices"):
         m1(**{k: v.to("cuda:0") for k, v in batch.items()})
+
+
+@pytest.mark.parametrize("name,B,mb", [("clip_fusion_hardened", 37, 16), ("clip_mtl_h256_hardened", 19, 128),
+                                       ("siglip_fusion_hardened", 12, 5)])
+def test_pooled_last_layer_is_bit_identical_to_all_rows(name, B, mb):
+    """Option pooled_last_layer: the last layer's out_proj / LN2 / MLP / final LN on the pooled rows only are row-wise
+    ops on gathered rows, so logits AND pooled tower outputs must not change by a single bit (HF clip :575-584,
+    :688-689 read one row per sample)."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, B, seed=300 + B, edge_rows=True).items()}
+    m = _make_module(kind, a, kw, sd)
+    m.set_option("micro_batch", mb)
+    for varlen in (0, 1):
+        m.set_option("varlen_text", varlen)
+        m.set_option("pooled_last_layer", 0)
+        y_all = m(**batch)["logits"].clone()
+        tp_all = m._engine.stage("text_pooled").clone()
+        vp_all = m._engine.stage("vision_pooled").clone()
+        n_all = m._engine.last_launch_count()
+        m.set_option("pooled_last_layer", 1)
+        y = m(**batch)["logits"]
+        assert torch.equal(y, y_all)
+        assert torch.equal(m._engine.stage("text_pooled"), tp_all)
+        assert torch.equal(m._engine.stage("vision_pooled"), vp_all)
+        assert m._engine.last_launch_count() > n_all          # the gather kernels ran

@@ -313,26 +313,42 @@ def main():
         pinned = {k: v.pin_memory() for k, v in host.items()}
         out_h = torch.empty((B, 5), dtype=torch.float32).pin_memory()
 
-        def estep():
-            return eng.forward_host(pinned["input_ids"], pinned["attention_mask"], pinned["pixel_values"],
-                                    pinned["text_present"], pinned["image_present"], out=out_h)
-        for _ in range(3):
-            estep()
-        sync_all()
-        ksteps = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(ksteps):
-            estep()
-        e1.record()
-        sync_all()
-        wall = (time.perf_counter() - t0) * 1e3
-        ems = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * ksteps / (ems.item() * 1e-3), "unit": "samples/s",
+        def timed_host(fn):
+            for _ in range(3):
+                fn()
+            sync_all()
+            ksteps = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(ksteps):
+                fn()
+            e1.record()
+            sync_all()
+            wall = (time.perf_counter() - t0) * 1e3
+            ems = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return world * B * ksteps / (ems.item() * 1e-3), ksteps
+
+        v, ksteps = timed_host(lambda: eng.forward_host(pinned["input_ids"], pinned["attention_mask"],
+                                                        pinned["pixel_values"], pinned["text_present"],
+                                                        pinned["image_present"], out=out_h))
+        e2e = {"value": v, "unit": "samples/s",
                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 5 * 4, "steps": ksteps,
                "api": "mmcm_forward_host (pinned host buffers, chunked H2D overlapped with the towers)"}
+        # the same call on raw uint8 HWC images: ToTensor + Normalize inside the im2col
+        img_u8 = torch.randint(0, 256, (B, a.image, a.image, 3), dtype=torch.uint8,
+                               generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
+        mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+        v8, k8 = timed_host(lambda: eng.forward_host_u8(pinned["input_ids"], pinned["attention_mask"], img_u8, mean, std,
+                                                        pinned["text_present"], pinned["image_present"], out=out_h))
+        if extras is None:
+            extras = {}
+        extras["e2e_u8"] = {"value": v8, "unit": "samples/s", "steps": k8,
+                            "h2d_bytes_per_step": in_bytes - host["pixel_values"].numel() * 4 + img_u8.numel(),
+                            "d2h_bytes_per_step": B * 5 * 4,
+                            "api": "mmcm_forward_host_u8 (uint8 HWC crops in; the eval transform's ToTensor + Normalize "
+                                   "run inside the patch im2col, logits bit-identical to the fp32-pixel call)"}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel family
     peaks = _peaks()

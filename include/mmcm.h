@@ -101,6 +101,22 @@ MMCM_API int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const in
                       const float* pixel_values, const float* text_present, const float* image_present,
                       int32_t B, int32_t S, float* logits_out, float* probs_out, void* stream);
 
+/* Same two calls with RAW uint8 pixels (the step immediately before the path).  pixels_u8 is
+ * [B, image, image, 3] (HWC, RGB), already resized / centre-cropped by the caller; ToTensor + Normalize of the eval
+ * transform (R/src/data/dataset.py:106-111) are applied in registers inside the patch im2col:
+ *     pixel_values[b,c,y,x] = (u8 / 255 - mean3[c]) / std3[c]      (fp32, torchvision's operation order)
+ * so the logits are bit-identical to mmcm_forward on the fp32 pixel_values that transform produces, the fp32 image
+ * never exists in HBM and the host ships 147 KB instead of 588 KB per 224 px sample.  mean3 / std3: 3 HOST floats.
+ * mmcm_forward_u8 takes device pointers (e.g. images decoded on the GPU), mmcm_forward_host_u8 host pointers. */
+MMCM_API int mmcm_forward_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                    const uint8_t* pixels_u8, const float* mean3, const float* std3, const float* text_present,
+                    const float* image_present, int32_t B, int32_t S, float* logits_out, float* probs_out,
+                    void* stream);
+MMCM_API int mmcm_forward_host_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                         const uint8_t* pixels_u8, const float* mean3, const float* std3, const float* text_present,
+                         const float* image_present, int32_t B, int32_t S, float* logits_out, float* probs_out,
+                         void* stream);
+
 /* Introspection ------------------------------------------------------------------------------ */
 /* Copies an intermediate of the LAST forward into dst (device fp32).  Names: "text_pooled",
  * "vision_pooled" (tower pooler_output, fp32 [B,D]), "text_hidden", "vision_hidden" (residual stream

@@ -964,7 +964,22 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
   return MMCM_OK;
 }
 
-static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_t st) {
+// Pixel source of a forward: the reference's normalised fp32 CHW `pixel_values`, or raw uint8 HWC images with the
+// Normalize constants (ToTensor + Normalize then happen inside the im2col, see im2col_u8_kernel).
+struct Pixels {
+  const float* f32 = nullptr;
+  const uint8_t* u8 = nullptr;
+  float mean[3] = {0.f, 0.f, 0.f}, std[3] = {1.f, 1.f, 1.f};
+  size_t bytes_per_sample(const mmcm_config& c) const { return (size_t)3 * c.image * c.image * (u8 ? 1 : 4); }
+  Pixels at(int64_t b, const mmcm_config& c) const {        // the same source advanced by b samples
+    Pixels r = *this;
+    const int64_t per = (int64_t)3 * c.image * c.image;
+    if (u8) r.u8 = u8 + b * per; else r.f32 = f32 + b * per;
+    return r;
+  }
+};
+
+static int run_vision(Eng* e, const Pixels& px, int n, float* pooled, cudaStream_t st) {
   const mmcm_config& c = e->cfg;
   const TowerW& t = e->vis;
   Arena& a = e->av;
@@ -976,7 +991,12 @@ static int run_vision(Eng* e, const float* px, int n, float* pooled, cudaStream_
   {
     const int64_t chunks = (int64_t)n * P * (Kp / 8);
     const int blocks = (int)((chunks + 255) / 256 < 148 * 16 ? (chunks + 255) / 256 : 148 * 16);
-    CK(launch_k(im2col_kernel, dim3(blocks), dim3(256), 0, st, px, e->im2col, n, c.image, c.patch));
+    if (px.u8)
+      CK(launch_k(im2col_u8_kernel, dim3(blocks), dim3(256), 0, st, px.u8, e->im2col, n, c.image, c.patch, px.mean[0],
+                  px.mean[1], px.mean[2], px.std[0], px.std[1], px.std[2],
+                  (int)((reinterpret_cast<uintptr_t>(px.u8) & 7) == 0)));
+    else
+      CK(launch_k(im2col_kernel, dim3(blocks), dim3(256), 0, st, px.f32, e->im2col, n, c.image, c.patch));
     CK(cudaGetLastError());
     S->launches++;
   }
@@ -1083,7 +1103,7 @@ static int ensure_static_io(Eng* e, int64_t B) {
   return MMCM_OK;
 }
 
-static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const float* px, const float* tp,
+static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const Pixels& px, const float* tp,
                           const float* ip, int B, int S, float* logits, float* probs, cudaStream_t st) {
   const mmcm_config& c = e->cfg;
   e->stats.launches = 0;
@@ -1102,7 +1122,6 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
     CK(cudaStreamWaitEvent(stx, e->ev_fork, 0));
     CK(cudaStreamWaitEvent(svx, e->ev_fork, 0));
   }
-  const int64_t px_per = (int64_t)3 * c.image * c.image;
   // enqueue the two towers' chunks alternately so that neither stream starves while the host is still launching
   for (int bt = 0, bv = 0; bt < B || bv < B;) {
     if (bt < B) {
@@ -1113,7 +1132,7 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
     }
     if (bv < B) {
       const int n = std::min(cv, B - bv);
-      CKR(run_vision(e, px + bv * px_per, n, e->pooled_v + (int64_t)bv * c.vis_hidden, svx));
+      CKR(run_vision(e, px.at(bv, c), n, e->pooled_v + (int64_t)bv * c.vis_hidden, svx));
       bv += n;
     }
   }
@@ -1299,7 +1318,9 @@ static int forward_graphed(Eng* e, const int64_t* ids, const int64_t* mask, cons
     cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
     int r = MMCM_OK;
     if (ce == cudaSuccess) {
-      r = forward_device(e, e->d_ids, mask ? e->d_mask : nullptr, e->d_px, e->d_tp, e->d_ip, B, S, e->d_logits,
+      Pixels spx;
+      spx.f32 = e->d_px;
+      r = forward_device(e, e->d_ids, mask ? e->d_mask : nullptr, spx, e->d_tp, e->d_ip, B, S, e->d_logits,
                          probs ? e->d_probs : nullptr, st);
       ce = cudaStreamEndCapture(st, &graph);
     }
@@ -1334,22 +1355,48 @@ int mmcm_forward(mmcm_handle h, const int64_t* input_ids, const int64_t* attenti
                         probs_out, st, &handled));
     if (handled) return MMCM_OK;
   }
-  return forward_device(h, input_ids, attention_mask, pixel_values, text_present, image_present, B, S, logits_out,
-                        probs_out, st);
+  Pixels px;
+  px.f32 = pixel_values;
+  return forward_device(h, input_ids, attention_mask, px, text_present, image_present, B, S, logits_out, probs_out, st);
 }
 
-int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
-                      const float* pixel_values, const float* text_present, const float* image_present, int32_t B,
-                      int32_t S, float* logits_out, float* probs_out, void* stream) {
-  CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
+static int make_u8_pixels(Pixels* px, const uint8_t* pixels_u8, const float* mean3, const float* std3) {
+  if (!mean3 || !std3) return fail(MMCM_EINVAL, "null mean / std");
+  px->u8 = pixels_u8;
+  for (int i = 0; i < 3; ++i) {
+    if (!(std3[i] > 0.f)) return fail(MMCM_EINVAL, "std[%d] must be positive", i);
+    px->mean[i] = mean3[i];
+    px->std[i] = std3[i];
+  }
+  return MMCM_OK;
+}
+
+int mmcm_forward_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask, const uint8_t* pixels_u8,
+                    const float* mean3, const float* std3, const float* text_present, const float* image_present,
+                    int32_t B, int32_t S, float* logits_out, float* probs_out, void* stream) {
+  CKR(check_forward_args(h, input_ids, pixels_u8, text_present, image_present, B, S, logits_out));
+  Pixels px;
+  CKR(make_u8_pixels(&px, pixels_u8, mean3, std3));
   CK(cudaSetDevice(h->device));
-  Eng* e = h;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return forward_device(h, input_ids, attention_mask, px, text_present, image_present, B, S, logits_out, probs_out,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+// host buffers in, host logits out; `hpx` points at HOST pixels (fp32 CHW or uint8 HWC)
+static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* attention_mask, const Pixels& hpx,
+                             const float* text_present, const float* image_present, int32_t B, int32_t S,
+                             float* logits_out, float* probs_out, cudaStream_t st) {
+  CK(cudaSetDevice(e->device));
   if (B == 0) return MMCM_OK;
   const mmcm_config& c = e->cfg;
-  const int64_t px_per = (int64_t)3 * c.image * c.image;
+  const size_t px_bytes = hpx.bytes_per_sample(c);
+  const char* hsrc = hpx.u8 ? reinterpret_cast<const char*>(hpx.u8) : reinterpret_cast<const char*>(hpx.f32);
   const int C = c.num_outputs;
   CKR(ensure_static_io(e, B));
+  Pixels dpx = hpx;                                          // device-side staging: the fp32 buffer doubles for uint8
+  if (hpx.u8) dpx.u8 = reinterpret_cast<const uint8_t*>(e->d_px); else dpx.f32 = e->d_px;
   // small inputs first, then the pixels in micro-batch chunks on the copy stream so that the H2D transfer of
   // chunk i+1 overlaps the towers of chunk i
   CK(cudaMemcpyAsync(e->d_ids, input_ids, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
@@ -1374,7 +1421,7 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   CK(cudaStreamWaitEvent(e->s_copy, e->ev_fork, 0));
   for (int ci = 0; ci < nchunks; ++ci) {
     const int b0 = ci * cv, n = std::min(cv, (int)B - b0);
-    CK(cudaMemcpyAsync(e->d_px + b0 * px_per, pixel_values + b0 * px_per, (size_t)n * px_per * 4,
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(e->d_px) + b0 * px_bytes, hsrc + b0 * px_bytes, (size_t)n * px_bytes,
                        cudaMemcpyHostToDevice, e->s_copy));
     CK(cudaEventRecord(e->ev_chunk[ci], e->s_copy));
   }
@@ -1393,7 +1440,7 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
     if (bv < B) {
       const int n = std::min(cv, (int)B - bv);
       CK(cudaStreamWaitEvent(e->s_vis, e->ev_chunk[ci], 0));
-      CKR(run_vision(e, e->d_px + bv * px_per, n, e->pooled_v + (int64_t)bv * c.vis_hidden, e->s_vis));
+      CKR(run_vision(e, dpx.at(bv, c), n, e->pooled_v + (int64_t)bv * c.vis_hidden, e->s_vis));
       bv += n;
       ++ci;
     }
@@ -1408,6 +1455,29 @@ int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* at
   if (probs_out) CK(cudaMemcpyAsync(probs_out, e->d_probs, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MMCM_OK;
+}
+
+extern "C" {
+
+int mmcm_forward_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                      const float* pixel_values, const float* text_present, const float* image_present, int32_t B,
+                      int32_t S, float* logits_out, float* probs_out, void* stream) {
+  CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
+  Pixels px;
+  px.f32 = pixel_values;
+  return forward_host_impl(h, input_ids, attention_mask, px, text_present, image_present, B, S, logits_out, probs_out,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mmcm_forward_host_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                         const uint8_t* pixels_u8, const float* mean3, const float* std3, const float* text_present,
+                         const float* image_present, int32_t B, int32_t S, float* logits_out, float* probs_out,
+                         void* stream) {
+  CKR(check_forward_args(h, input_ids, pixels_u8, text_present, image_present, B, S, logits_out));
+  Pixels px;
+  CKR(make_u8_pixels(&px, pixels_u8, mean3, std3));
+  return forward_host_impl(h, input_ids, attention_mask, px, text_present, image_present, B, S, logits_out, probs_out,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity, int64_t* numel_out, void* stream) {

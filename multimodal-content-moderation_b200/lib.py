@@ -40,6 +40,8 @@ _SIGS = {
     "mmcm_finalize_weights": (C.c_int, [_P]),
     "mmcm_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_forward_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "mmcm_forward_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "mmcm_forward_host_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_get_stage": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "mmcm_last_launch_count": (C.c_int64, [_P]),
     "mmcm_gemm_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -109,6 +109,21 @@ class _B200ScoringModule(nn.Module):
             return eng.forward(input_ids, attention_mask, pixel_values, text_present, image_present)
 
     @torch.no_grad()
+    def forward_u8(self, input_ids, attention_mask, images_u8, text_present, image_present, image_mean, image_std,
+                   want_probs: bool = False):
+        """Forward on raw uint8 [B,H,W,3] images (already resized / cropped): the eval transform's ToTensor +
+        Normalize (R/src/data/dataset.py:106-111) run inside the patch im2col.  Returns logits (and probs)."""
+        if not input_ids.is_cuda:
+            raise RuntimeError("inputs must be CUDA tensors: the B200 scoring path has no CPU fallback")
+        dev = input_ids.device.index if input_ids.device.index is not None else torch.cuda.current_device()
+        if self._device_index() != dev:
+            raise RuntimeError("model and inputs are on different devices")
+        eng = self._ensure_engine(dev)
+        with torch.cuda.device(dev):
+            return eng.forward_u8(input_ids, attention_mask, images_u8, image_mean, image_std, text_present,
+                                  image_present, want_probs=want_probs)
+
+    @torch.no_grad()
     def predict_proba(self, **batch) -> torch.Tensor:
         """sigmoid(logits) fused into the head kernel (the callers' NumPy post-processing, inference.py:218)."""
         ids = batch["input_ids"]

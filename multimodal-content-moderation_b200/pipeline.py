@@ -3,8 +3,8 @@
 The reference scores one sample per forward: `MultiModalClassifier.predict_batch` is a Python loop over `predict`
 (R/scripts/inference.py:256-270) and SageMaker's `predict_fn` loops over instances (R/sagemaker/inference.py:241-296).
 `BatchedScorer` takes the already tokenised ids and the already resized / cropped uint8 images of MANY requests and
-runs them as one batch: uint8 -> ToTensor/Normalize on the GPU (prepost.preprocess_u8), one forward, fused
-sigmoid / thresholds / any_harmful (prepost.postprocess).  Tokenisation, JPEG decode and PIL's antialiased resize stay
+runs them as one batch: one forward on the raw uint8 images (ToTensor/Normalize inside the patch im2col,
+`mmcm_forward_u8`), fused sigmoid / thresholds / any_harmful (prepost.postprocess).  Tokenisation, JPEG decode and PIL's antialiased resize stay
 on the CPU exactly as in the reference (R/src/data/dataset.py:106-165).
 """
 from __future__ import annotations
@@ -47,13 +47,15 @@ class BatchedScorer:
         outs: List[Dict[str, torch.Tensor]] = []
         for s in range(0, N, self.max_batch):
             e = min(s + self.max_batch, N)
+            ids = input_ids[s:e].to(dev, non_blocking=True)
+            mask = attention_mask[s:e].to(dev, non_blocking=True)
             if images_u8 is None:
                 px = torch.zeros(e - s, 3, a.image, a.image, device=dev)
+                logits = self.model(input_ids=ids, attention_mask=mask, pixel_values=px, text_present=tp[s:e],
+                                    image_present=ip[s:e])["logits"]
             else:
-                px = prepost.preprocess_u8(images_u8[s:e].to(dev, non_blocking=True), self.mean, self.std)
-            logits = self.model(input_ids=input_ids[s:e].to(dev, non_blocking=True),
-                                attention_mask=attention_mask[s:e].to(dev, non_blocking=True), pixel_values=px,
-                                text_present=tp[s:e], image_present=ip[s:e])["logits"]
+                logits = self.model.forward_u8(ids, mask, images_u8[s:e].to(dev, non_blocking=True), tp[s:e], ip[s:e],
+                                               self.mean, self.std)
             outs.append(prepost.postprocess(logits, self.thresholds))
         return {k: torch.cat([o[k] for o in outs], dim=0) for k in ("probs", "labels", "any_harmful")}
 

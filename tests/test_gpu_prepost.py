@@ -97,3 +97,50 @@ def test_batched_scorer_equals_per_sample_reference_flow():
     # no image at all -> image_present = 0 path
     res2 = scorer.score(b["input_ids"][:4], b["attention_mask"][:4], None)
     assert res2["probs"].shape == (4, 5)
+
+
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "siglip_fusion_hardened", "clip_mtl_h256_hardened"])
+def test_forward_u8_is_bit_identical_to_transform_then_forward(name):
+    """mmcm_forward_u8 / mmcm_forward_host_u8 (ToTensor + Normalize inside the im2col) == the reference's transform tail
+    (R/src/data/dataset.py:106-111, computed by torch on the CPU) followed by the fp32-pixel forward -- every bit."""
+    from conftest import build_case
+    from test_gpu_forward import _make_module
+    from mmcm_b200 import synthetic as syn
+    from oracle import prepost_oracle as orc
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    B = 11
+    b = syn.make_inputs(a, B, seed=70, edge_rows=True)
+    img = torch.randint(0, 256, (B, a.image, a.image, 3), generator=torch.Generator().manual_seed(4), dtype=torch.uint8)
+    img[0] = 0
+    img[1] = 255
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    dbatch = {k: v.to("cuda:0") for k, v in b.items()}
+    ref = m(**dict(dbatch, pixel_values=orc.to_tensor_normalize(img, mean, std).cuda()))["logits"]
+    got, probs = m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], img.cuda(), dbatch["text_present"],
+                              dbatch["image_present"], mean, std, want_probs=True)
+    assert torch.equal(got, ref)
+    assert torch.equal(probs, torch.sigmoid(ref)) or (probs - torch.sigmoid(ref)).abs().max().item() < 1e-6
+    # a pixel buffer that is not 8-byte aligned takes the byte-load branch of the kernel
+    flat = torch.empty(img.numel() + 3, dtype=torch.uint8, device="cuda:0")
+    odd = flat[3:].view_as(img)
+    odd.copy_(img)
+    assert odd.data_ptr() % 8 != 0
+    assert torch.equal(m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], odd, dbatch["text_present"],
+                                    dbatch["image_present"], mean, std), ref)
+    # host entry point, chunked H2D of the uint8 images
+    eng = m._engine
+    m.set_option("micro_batch", 4)
+    host = eng.forward_host_u8(b["input_ids"], b["attention_mask"], img.pin_memory(), mean, std, b["text_present"],
+                               b["image_present"])
+    assert torch.equal(host, ref.cpu())
+    # argument errors: wrong size mirrors HF clip :204-207, wrong dtype / std
+    with pytest.raises(ValueError, match="doesn't match model"):
+        m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], img[:, :32].cuda(), dbatch["text_present"],
+                     dbatch["image_present"], mean, std)
+    with pytest.raises(ValueError):
+        m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], img.cuda().float(), dbatch["text_present"],
+                     dbatch["image_present"], mean, std)
+    with pytest.raises(ValueError, match="std"):
+        m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], img.cuda(), dbatch["text_present"],
+                     dbatch["image_present"], mean, [0.0, 1.0, 1.0])

@@ -82,6 +82,17 @@ MMCM_API int mmcm_load_weight(mmcm_handle h, const char* key, const float* src, 
 /* Verifies that every tensor of the configured model was loaded and builds the TMA descriptors. */
 MMCM_API int mmcm_finalize_weights(mmcm_handle h);
 
+/* Packed weight file (checkpoint -> repacked bf16 blob).  mmcm_save_packed writes the handle's
+ * finalized, repacked weight set (bf16 GEMM operands, fp32 norms / biases / embeddings / heads) with the handle's
+ * mmcm_config and a checksum into one file; mmcm_load_packed maps such a file and copies it straight into a handle
+ * created with the SAME config (replaces the mmcm_load_weight loop + mmcm_finalize_weights: no fp32 checkpoint read,
+ * no repack); mmcm_packed_config reads the config a file was packed for, so a caller can mmcm_create from the file
+ * alone.  Replaces the model.safetensors load of R/scripts/evaluate.py:139-151 on every start after the first.
+ * Errors: MMCM_EINVAL for a missing / foreign / corrupt file or a config mismatch. */
+MMCM_API int mmcm_save_packed(mmcm_handle h, const char* path);
+MMCM_API int mmcm_load_packed(mmcm_handle h, const char* path);
+MMCM_API int mmcm_packed_config(const char* path, mmcm_config* cfg_out);
+
 /* The hot path.  Replaces MultiModalFusionClassifier.forward / MultiTaskClassifier.forward
  * (fusion.py:157-216, multitask.py:156-207): all pointers are DEVICE pointers.
  *   input_ids      int64 [B,S]            attention_mask int64 [B,S] or NULL (== all ones)

@@ -8,10 +8,11 @@ Public surface (mirrors `src.models` of the reference, R/src/models/__init__.py:
 
 Importing this package never touches CUDA; the extension is loaded (and, if stale, rebuilt) on first use.
 """
-from . import arch, build, lib, prepost, sharding, synthetic  # noqa: F401
+from . import arch, build, checkpoint, lib, prepost, sharding, synthetic  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .checkpoint import PackedScorer, load_checkpoint  # noqa: F401
 from .pipeline import BatchedScorer  # noqa: F401
 from .modules import FocalWithLogitsLoss, MultiModalFusionClassifier, MultiTaskClassifier  # noqa: F401
 
-__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "BatchedScorer", "arch", "build",
-           "lib", "prepost", "sharding", "synthetic"]
+__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "BatchedScorer", "PackedScorer", "load_checkpoint", "arch", "build",
+           "checkpoint", "lib", "prepost", "sharding", "synthetic"]

@@ -15,8 +15,14 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -459,6 +465,10 @@ struct mmcm_handle_s {
   std::vector<void*> allocs;
   std::unordered_map<std::string, Slot> slots;
   bool finalized = false;
+  // every buffer of the repacked weight set, in allocation order (a pure function of cfg): the packed weight file
+  struct WBuf { void* ptr; size_t bytes; };
+  std::vector<WBuf> wbufs;
+  bool recording_weights = false;
 
   TowerW text, vis;
   // text extras
@@ -517,6 +527,7 @@ static int dalloc(Eng* e, T** out, int64_t count) {
   if (err != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc(%lld bytes) failed: %s", (long long)(count * sizeof(T)),
                                       cudaGetErrorString(err));
   e->allocs.push_back(p);
+  if (e->recording_weights) e->wbufs.push_back({p, (size_t)count * sizeof(T)});
   *out = reinterpret_cast<T*>(p);
   return MMCM_OK;
 }
@@ -1177,7 +1188,9 @@ int mmcm_create(const mmcm_config* cfg, int device, mmcm_handle* out) {
   Eng* e = new Eng();
   e->cfg = *cfg;
   e->device = device;
+  e->recording_weights = true;
   int r = setup_weights(e);
+  e->recording_weights = false;
   if (r == MMCM_OK) {
     cudaError_t ce = cudaSuccess;
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->s_text, cudaStreamNonBlocking);
@@ -1287,6 +1300,154 @@ int mmcm_finalize_weights(mmcm_handle h) {
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
   }
+  h->finalized = true;
+  return MMCM_OK;
+}
+
+// ---- packed weight file -----------------------------------------------------------------------
+// The repacked weight set (bf16 GEMM operands, Q|K|V fused, dh^-1/2 folded, fp32 everything else) as one blob that a
+// later process maps and copies straight into the handle's buffers: no fp32 checkpoint read, no repack kernels, no
+// fp32 master copy.  Layout: PackedHeader | sizes[n_bufs] | pad to 4096 | buffers, each 256-byte aligned, in the
+// handle's allocation order (a pure function of mmcm_config, which the header carries and the loader compares).
+struct PackedHeader {
+  char magic[8];            // "MMCMPK01"
+  uint32_t header_bytes;    // sizeof(PackedHeader)
+  uint32_t cfg_bytes;       // sizeof(mmcm_config)
+  uint64_t n_bufs;
+  uint64_t payload_offset;  // from the start of the file
+  uint64_t payload_bytes;
+  uint64_t checksum;        // packed_checksum over the payload
+  mmcm_config cfg;
+};
+static const char kPackedMagic[8] = {'M', 'M', 'C', 'M', 'P', 'K', '0', '1'};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static uint64_t packed_checksum(const unsigned char* p, size_t n, uint64_t h = 0x9E3779B97F4A7C15ull) {
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29;
+  }
+  for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h;
+}
+
+int mmcm_save_packed(mmcm_handle h, const char* path) {
+  if (!h || !path) return fail(MMCM_EINVAL, "null argument");
+  if (!h->finalized) return fail(MMCM_ESTATE, "weights are not finalized (nothing to save)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  PackedHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, kPackedMagic, 8);
+  hd.header_bytes = sizeof(PackedHeader);
+  hd.cfg_bytes = sizeof(mmcm_config);
+  hd.n_bufs = h->wbufs.size();
+  hd.cfg = h->cfg;
+  std::vector<uint64_t> sizes;
+  size_t payload = 0;
+  for (const auto& b : h->wbufs) {
+    sizes.push_back(b.bytes);
+    payload += align_up(b.bytes, 256);
+  }
+  hd.payload_offset = align_up(sizeof(PackedHeader) + sizes.size() * 8, 4096);
+  hd.payload_bytes = payload;
+  std::vector<unsigned char> host(payload, 0);
+  size_t off = 0;
+  for (const auto& b : h->wbufs) {
+    CK(cudaMemcpy(host.data() + off, b.ptr, b.bytes, cudaMemcpyDeviceToHost));
+    off += align_up(b.bytes, 256);
+  }
+  hd.checksum = packed_checksum(host.data(), payload);
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(MMCM_EINVAL, "cannot open '%s' for writing: %s", tmp.c_str(), strerror(errno));
+  std::vector<unsigned char> head(hd.payload_offset, 0);
+  memcpy(head.data(), &hd, sizeof(hd));
+  memcpy(head.data() + sizeof(hd), sizes.data(), sizes.size() * 8);
+  bool ok = fwrite(head.data(), 1, head.size(), f) == head.size() && fwrite(host.data(), 1, payload, f) == payload;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {
+    remove(tmp.c_str());
+    return fail(MMCM_EINVAL, "writing '%s' failed: %s", path, strerror(errno));
+  }
+  return MMCM_OK;
+}
+
+// maps the file read-only; *base / *len describe the mapping the caller must munmap
+static int map_packed(const char* path, const unsigned char** base, size_t* len, const PackedHeader** hd) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(MMCM_EINVAL, "cannot open packed weight file '%s': %s", path, strerror(errno));
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(PackedHeader)) {
+    close(fd);
+    return fail(MMCM_EINVAL, "'%s' is not a packed weight file (too short)", path);
+  }
+  void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(MMCM_EINVAL, "mmap of '%s' failed: %s", path, strerror(errno));
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(m);
+  const size_t n = (size_t)st.st_size;
+  if (memcmp(h->magic, kPackedMagic, 8) != 0 || h->header_bytes != sizeof(PackedHeader) ||
+      h->cfg_bytes != sizeof(mmcm_config) || h->n_bufs > (1u << 20) ||
+      sizeof(PackedHeader) + h->n_bufs * 8 > h->payload_offset || h->payload_offset > n ||
+      h->payload_bytes != n - h->payload_offset) {
+    munmap(m, n);
+    return fail(MMCM_EINVAL, "'%s' is not a packed weight file of this library version (bad header)", path);
+  }
+  *base = reinterpret_cast<const unsigned char*>(m);
+  *len = n;
+  *hd = h;
+  return MMCM_OK;
+}
+
+int mmcm_packed_config(const char* path, mmcm_config* cfg_out) {
+  if (!path || !cfg_out) return fail(MMCM_EINVAL, "null argument");
+  const unsigned char* base = nullptr;
+  size_t len = 0;
+  const PackedHeader* hd = nullptr;
+  CKR(map_packed(path, &base, &len, &hd));
+  *cfg_out = hd->cfg;
+  munmap(const_cast<unsigned char*>(base), len);
+  return MMCM_OK;
+}
+
+int mmcm_load_packed(mmcm_handle h, const char* path) {
+  if (!h || !path) return fail(MMCM_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  const unsigned char* base = nullptr;
+  size_t len = 0;
+  const PackedHeader* hd = nullptr;
+  CKR(map_packed(path, &base, &len, &hd));
+  int rc = MMCM_OK;
+  const uint64_t* sizes = reinterpret_cast<const uint64_t*>(base + sizeof(PackedHeader));
+  if (memcmp(&hd->cfg, &h->cfg, sizeof(mmcm_config)) != 0)
+    rc = fail(MMCM_EINVAL, "'%s' was packed for a different model configuration than this handle", path);
+  else if (hd->n_bufs != h->wbufs.size())
+    rc = fail(MMCM_EINVAL, "'%s' holds %llu buffers, this library version lays out %zu", path,
+              (unsigned long long)hd->n_bufs, h->wbufs.size());
+  size_t total = 0;
+  for (size_t i = 0; rc == MMCM_OK && i < h->wbufs.size(); ++i) {
+    if (sizes[i] != h->wbufs[i].bytes) rc = fail(MMCM_EINVAL, "'%s': buffer %zu has another size than this library lays out", path, i);
+    total += align_up(h->wbufs[i].bytes, 256);
+  }
+  if (rc == MMCM_OK && total != hd->payload_bytes) rc = fail(MMCM_EINVAL, "'%s': payload size mismatch", path);
+  if (rc == MMCM_OK && packed_checksum(base + hd->payload_offset, hd->payload_bytes) != hd->checksum)
+    rc = fail(MMCM_EINVAL, "'%s': checksum mismatch (file is corrupt)", path);
+  if (rc == MMCM_OK) {
+    cudaError_t ce = cudaDeviceSynchronize();
+    size_t off = hd->payload_offset;
+    for (size_t i = 0; ce == cudaSuccess && i < h->wbufs.size(); ++i) {
+      ce = cudaMemcpy(h->wbufs[i].ptr, base + off, h->wbufs[i].bytes, cudaMemcpyHostToDevice);
+      off += align_up(h->wbufs[i].bytes, 256);
+    }
+    if (ce != cudaSuccess) rc = fail(MMCM_ECUDA, "H2D copy of packed weights failed: %s", cudaGetErrorString(ce));
+  }
+  munmap(const_cast<unsigned char*>(base), len);
+  CKR(rc);
+  for (auto& kv : h->slots) kv.second.loaded = true;
   h->finalized = true;
   return MMCM_OK;
 }
@@ -1546,12 +1707,12 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "streams") {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
-  } else if (n == "pdl") g_pdl = value != 0;
-  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;
-  else if (n == "attention_impl") {
+  } else if (n == "pdl") g_pdl = value != 0;                    // process-wide: programmatic dependent launch on/off
+  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;    // process-wide: TMA store / reduce-add epilogue of the pair GEMM
+  else if (n == "attention_impl") {                             // process-wide
     if (value < 0 || value > 2) return fail(MMCM_EINVAL, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05 for T <= 128)");
     g_attention_impl = (int)value;
-  }   // process-wide: TMA store / reduce-add epilogue of the pair GEMM   // process-wide: programmatic dependent launch on/off
+  }
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;

@@ -28,6 +28,15 @@ def _cfg_struct(a: A.ArchCfg, head: int, num_outputs: int, fusion_dim: int, head
     return c
 
 
+def _arch_from_struct(c: L.MmcmConfig) -> A.ArchCfg:
+    """Inverse of `_cfg_struct` for the shape fields (a packed weight file carries the struct, not the dataclass)."""
+    return A.ArchCfg(
+        backend=c.backend,
+        text=A.TowerCfg(c.text_hidden, c.text_heads, c.text_layers, c.text_ffn, c.text_eps, c.text_act),
+        vision=A.TowerCfg(c.vis_hidden, c.vis_heads, c.vis_layers, c.vis_ffn, c.vis_eps, c.vis_act),
+        vocab=c.vocab, max_pos=c.max_pos, eos_id=c.eos_id, image=c.image, patch=c.patch, proj_dim=c.proj_dim)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -68,6 +77,25 @@ class Engine:
 
     def set_option(self, name: str, value: int) -> None:
         L.check(self.lib.mmcm_set_option(self._h, name.encode(), int(value)))
+
+    # ------------------------------------------------------------------ packed weight file
+    def save_packed(self, path: str) -> None:
+        """Write the repacked (bf16 / fp32) weight set of this engine as one blob (`mmcm_save_packed`)."""
+        L.check(self.lib.mmcm_save_packed(self._h, str(path).encode()))
+
+    def load_packed(self, path: str) -> None:
+        """Fill this engine from a blob written by `save_packed` for the same configuration."""
+        L.check(self.lib.mmcm_load_packed(self._h, str(path).encode()))
+
+    @classmethod
+    def from_packed(cls, path: str, device: int = 0) -> "Engine":
+        """Build an engine from a packed weight file alone: configuration from its header, weights by one copy."""
+        lib = L.load()
+        cfg = L.MmcmConfig()
+        L.check(lib.mmcm_packed_config(str(path).encode(), C.byref(cfg)))
+        eng = cls(_arch_from_struct(cfg), cfg.head, cfg.num_outputs, cfg.fusion_dim, cfg.head_hidden_dim, device)
+        eng.load_packed(path)
+        return eng
 
     # ------------------------------------------------------------------ hot path
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], pixel_values: torch.Tensor,

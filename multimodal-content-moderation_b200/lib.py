@@ -38,6 +38,9 @@ _SIGS = {
     "mmcm_destroy": (C.c_int, [_P]),
     "mmcm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "mmcm_finalize_weights": (C.c_int, [_P]),
+    "mmcm_save_packed": (C.c_int, [_P, C.c_char_p]),
+    "mmcm_load_packed": (C.c_int, [_P, C.c_char_p]),
+    "mmcm_packed_config": (C.c_int, [C.c_char_p, _P]),
     "mmcm_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_forward_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_forward_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),

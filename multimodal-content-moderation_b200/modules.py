@@ -79,6 +79,10 @@ class _B200ScoringModule(nn.Module):
         self._ensure_engine(self._device_index())
         self._engine.set_option(name, value)
 
+    def save_packed(self, path: str) -> None:
+        """Write the extension's repacked weight set as one blob (`mmcm_save_packed`; see checkpoint.PackedScorer)."""
+        self._ensure_engine(self._device_index()).save_packed(path)
+
     def _device_index(self) -> int:
         p = next(self.parameters())
         if not p.is_cuda:

@@ -102,3 +102,41 @@ def test_empty_batch_is_a_no_op():
     y = eng.forward(ids, ids, px, f, f)
     assert y.shape == (0, 5)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened", "siglip_fusion_hardened"])
+def test_packed_weight_file_round_trip(name, tmp_path):
+    """mmcm_save_packed -> mmcm_packed_config / mmcm_load_packed in a fresh handle: bit-identical logits without the
+    fp32 state dict; a config mismatch or a flipped byte is refused."""
+    import mmcm_b200 as P
+    from conftest import build_case
+    from test_gpu_forward import _make_module
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 9, seed=61, edge_rows=True).items()}
+    ref = m(**batch)["logits"].clone()
+    path = tmp_path / "packed.bin"
+    m.save_packed(str(path))
+    bf16_bytes = sum(v.numel() for v in sd.values()) * 2
+    assert bf16_bytes < path.stat().st_size < 2.6 * bf16_bytes          # bf16 matrices + fp32 embeddings / heads
+    scorer = P.PackedScorer(path, "cuda:0")
+    out = scorer(**batch)
+    assert out["loss"] is None and torch.equal(out["logits"], ref)
+    ea = scorer.engine.arch                                             # rebuilt from the header (eps went through fp32)
+    assert scorer.engine.num_outputs == ref.shape[1]
+    assert (ea.backend, ea.image, ea.patch, ea.max_pos, ea.vocab, ea.text.hidden, ea.vision.hidden, ea.text.layers) == \
+        (a.backend, a.image, a.patch, a.max_pos, a.vocab, a.text.hidden, a.vision.hidden, a.text.layers)
+    # a handle with another configuration refuses the file
+    other = "clip_mtl_h256_hardened" if name != "clip_mtl_h256_hardened" else "clip_fusion_hardened"
+    kind2, a2, kw2, sd2, _, _ = build_case(other)
+    m2 = _make_module(kind2, a2, kw2, sd2)
+    with pytest.raises(ValueError, match="different model configuration"):
+        m2._ensure_engine(0).load_packed(str(path))
+    # corruption is detected by the checksum
+    raw = bytearray(path.read_bytes())
+    raw[len(raw) // 2] ^= 0x40
+    bad = tmp_path / "corrupt.bin"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(ValueError, match="checksum"):
+        P.PackedScorer(bad, "cuda:0")

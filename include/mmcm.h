@@ -196,6 +196,15 @@ MMCM_API int mmcm_attention(const void* qkv, const uint8_t* key_valid, int32_t B
  * torchvision.  mean3 / std3 are HOST pointers to 3 floats. W % 4 == 0. */
 MMCM_API int mmcm_preprocess_u8(const uint8_t* hwc, int32_t B, int32_t H, int32_t W, const float* mean3,
                                 const float* std3, float* chw_out, void* stream);
+/* T.Resize(size, antialias=True) + T.CenterCrop((size, size)) of the eval transform (R/src/data/dataset.py:106-108)
+ * for B decoded uint8 RGB images of DIFFERENT sizes: src = device buffer holding the HWC images back to back,
+ * offsets[b] = byte offset of image b, heights / widths = its size (three HOST arrays of length B); out = device
+ * [B, size, size, 3] uint8, ready for mmcm_forward_u8.  The arithmetic is Pillow's Image.resize(BILINEAR) -- tap windows
+ * and weights in double precision, 22-bit fixed-point coefficients, horizontal pass rounded to uint8, then the vertical
+ * pass -- so the crops are byte-identical to what torchvision produces from a PIL image.  Only the cropped region is
+ * computed.  Grid dimension y carries B: B <= 65535 per call. */
+MMCM_API int mmcm_resize_crop_u8(const uint8_t* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                        int32_t B, int32_t size, uint8_t* out, void* stream);
 /* probs = 1/(1+exp(-logits)); decisions[b,c] = probs >= thresholds[c]; any[b] = OR_c decisions
  * (R/scripts/inference.py:218-232); when labels != NULL, confusion_accum[c*4 + {0,1,2,3}] += {TP,FP,FN,TN}
  * (the counts behind f1/precision/recall of R/src/training/metrics.py:180-205).  Outputs may be NULL. C <= 64. */

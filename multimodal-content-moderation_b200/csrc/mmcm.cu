@@ -1778,6 +1778,56 @@ int mmcm_preprocess_u8(const uint8_t* hwc, int32_t B, int32_t H, int32_t W, cons
   return MMCM_OK;
 }
 
+int mmcm_resize_crop_u8(const uint8_t* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                        int32_t B, int32_t size, uint8_t* out, void* stream) {
+  if (!src || !offsets || !heights || !widths || !out) return fail(MMCM_EINVAL, "null pointer");
+  if (B < 0 || B > 65535 || size <= 0 || size > 1024)
+    return fail(MMCM_EINVAL, "resize_crop_u8: bad batch %d (<= 65535 per call) or size %d (<= 1024)", B, size);
+  if (B == 0) return MMCM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int kh = 3, kv = 3;
+  double max_scale_v = 1.0;
+  for (int b = 0; b < B; ++b) {
+    if (heights[b] <= 0 || widths[b] <= 0 || heights[b] > 32768 || widths[b] > 32768 || offsets[b] < 0)
+      return fail(MMCM_EINVAL, "resize_crop_u8: image %d has bad geometry %dx%d", b, heights[b], widths[b]);
+    ResizeGeom g;
+    resize_geometry(heights[b], widths[b], size, g);
+    kh = std::max(kh, g.ksize_h);
+    kv = std::max(kv, g.ksize_v);
+    max_scale_v = std::max(max_scale_v, g.scale_v);
+  }
+  // rows per CTA: as many as the shared-memory tile allows (16 for every realistic photo)
+  int rows = 16, max_src_rows = 0;
+  size_t smem = 0;
+  for (;; rows >>= 1) {
+    max_src_rows = resize_strip_rows(max_scale_v, rows);
+    smem = sizeof(int) * ((size_t)2 * size + (size_t)size * kh + 2 * rows + (size_t)rows * kv) +
+           (size_t)max_src_rows * size * 3;
+    if (smem <= 200 * 1024 || rows == 1) break;
+  }
+  if (smem > 200 * 1024)
+    return fail(MMCM_EINVAL, "resize_crop_u8: a %.1fx downscale needs %zu bytes of shared memory per CTA", max_scale_v, smem);
+  static AttrOnce once;
+  if (once.need()) CK(cudaFuncSetAttribute(resize_crop_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  // per-image metadata: one stream-ordered scratch allocation (offsets | heights | widths)
+  char* meta = nullptr;
+  const size_t mbytes = (size_t)B * (8 + 4 + 4);
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&meta), mbytes, st));
+  long long* d_off = reinterpret_cast<long long*>(meta);
+  int* d_h = reinterpret_cast<int*>(meta + (size_t)B * 8);
+  int* d_w = d_h + B;
+  cudaError_t ce = cudaMemcpyAsync(d_off, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_h, heights, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_w, widths, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess)
+    ce = launch_k(resize_crop_u8_kernel, dim3((size + rows - 1) / rows, B), dim3(256), smem, st, src,
+                  (const long long*)d_off, (const int*)d_h, (const int*)d_w, (int)size, rows, kh, kv, max_src_rows, out);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  cudaFreeAsync(meta, st);
+  if (ce != cudaSuccess) return fail(MMCM_ECUDA, "resize_crop_u8 failed: %s", cudaGetErrorString(ce));
+  return MMCM_OK;
+}
+
 int mmcm_postprocess(const float* logits, const float* thresholds, const float* labels, int32_t B, int32_t C,
                      float* probs_out, uint8_t* decisions_out, uint8_t* any_out, uint64_t* confusion_accum,
                      void* stream) {

@@ -57,6 +57,7 @@ _SIGS = {
     "mmcm_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mmcm_cast_bf16": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),
     "mmcm_debug_set_gemm_trace": (C.c_int, [_P]),
+    "mmcm_resize_crop_u8": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "mmcm_preprocess_u8": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "mmcm_postprocess": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
 }

@@ -2,10 +2,11 @@
 
 The reference scores one sample per forward: `MultiModalClassifier.predict_batch` is a Python loop over `predict`
 (R/scripts/inference.py:256-270) and SageMaker's `predict_fn` loops over instances (R/sagemaker/inference.py:241-296).
-`BatchedScorer` takes the already tokenised ids and the already resized / cropped uint8 images of MANY requests and
-runs them as one batch: one forward on the raw uint8 images (ToTensor/Normalize inside the patch im2col,
-`mmcm_forward_u8`), fused sigmoid / thresholds / any_harmful (prepost.postprocess).  Tokenisation, JPEG decode and PIL's antialiased resize stay
-on the CPU exactly as in the reference (R/src/data/dataset.py:106-165).
+`BatchedScorer` takes the already tokenised ids and the uint8 images of MANY requests -- either already resized /
+cropped `[N,H,W,3]`, or a list of decoded images of any sizes, which `prepost.resize_crop_u8` resizes and crops on the
+GPU byte-identically to Pillow -- and runs them as one batch: one forward on the raw uint8 images (ToTensor/Normalize inside the patch im2col,
+`mmcm_forward_u8`), fused sigmoid / thresholds / any_harmful (prepost.postprocess).  Tokenisation and JPEG decode stay on the CPU exactly as in the
+reference (R/src/data/dataset.py:106-165).
 """
 from __future__ import annotations
 
@@ -34,7 +35,8 @@ class BatchedScorer:
     def score(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, images_u8: Optional[torch.Tensor],
               text_present: Optional[torch.Tensor] = None, image_present: Optional[torch.Tensor] = None
               ) -> Dict[str, torch.Tensor]:
-        """input_ids / attention_mask [N,S] int64, images_u8 [N,H,W,3] uint8 (or None: no images at all).
+        """input_ids / attention_mask [N,S] int64; images_u8 [N,H,W,3] uint8 crops, or a list of N decoded uint8
+        [H_i,W_i,3] images of any sizes (resized + centre-cropped on the GPU), or None: no images at all.
         Returns probs [N,C], labels [N,C] bool, any_harmful [N] bool -- the fields of inference.py:220-232."""
         N = input_ids.shape[0]
         dev = self.device
@@ -54,8 +56,11 @@ class BatchedScorer:
                 logits = self.model(input_ids=ids, attention_mask=mask, pixel_values=px, text_present=tp[s:e],
                                     image_present=ip[s:e])["logits"]
             else:
-                logits = self.model.forward_u8(ids, mask, images_u8[s:e].to(dev, non_blocking=True), tp[s:e], ip[s:e],
-                                               self.mean, self.std)
+                if isinstance(images_u8, (list, tuple)):                 # raw decoded images: Resize + CenterCrop here
+                    crops = prepost.resize_crop_u8(images_u8[s:e], a.image, device=dev)
+                else:
+                    crops = images_u8[s:e].to(dev, non_blocking=True)
+                logits = self.model.forward_u8(ids, mask, crops, tp[s:e], ip[s:e], self.mean, self.std)
             outs.append(prepost.postprocess(logits, self.thresholds))
         return {k: torch.cat([o[k] for o in outs], dim=0) for k in ("probs", "labels", "any_harmful")}
 

@@ -1,5 +1,7 @@
 """Host-side mirror of the callers' pre-/post-processing around the forward, on the GPU.
 
+    resize_crop_u8  Resize(size, antialias=True) + CenterCrop(size) of the same transform (dataset.py:106-108) on decoded
+                    uint8 RGB images of different sizes -- Pillow's fixed-point bilinear resampler, byte-identical
     preprocess_u8   ToTensor + Normalize of `SocialHarmDataset.eval_tf` (R/src/data/dataset.py:106-111)
     postprocess     sigmoid -> per-class thresholds -> any_harmful (R/scripts/inference.py:218-232) and the per-class
                     confusion counts behind compute_detailed_metrics (R/src/training/metrics.py:164-215)
@@ -16,6 +18,38 @@ from . import lib as L
 
 def _stream(t: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def resize_crop_u8(images: Sequence[torch.Tensor], size: int, device=None) -> torch.Tensor:
+    """Decoded RGB images (uint8 [H_i, W_i, 3] tensors, CPU or CUDA, any sizes) -> CUDA uint8 [B, size, size, 3]:
+    shorter side resized to `size` like `Image.resize(BILINEAR)`, then the centre crop.  Feed the result to
+    `model.forward_u8` / `preprocess_u8`."""
+    if len(images) == 0:
+        raise ValueError("resize_crop_u8 needs at least one image")
+    for im in images:
+        if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[-1] != 3:
+            raise ValueError("resize_crop_u8 expects uint8 [H, W, 3] tensors")
+    if device is None:
+        device = next((im.device for im in images if im.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("resize_crop_u8 runs on the GPU: no CPU fallback")
+    B = len(images)
+    flat = torch.cat([im.contiguous().reshape(-1) for im in images]).to(device, non_blocking=True)
+    sizes = [int(im.shape[0]) * int(im.shape[1]) * 3 for im in images]
+    offs, acc = [], 0
+    for n in sizes:
+        offs.append(acc)
+        acc += n
+    offsets = (C.c_int64 * B)(*offs)
+    heights = (C.c_int32 * B)(*[int(im.shape[0]) for im in images])
+    widths = (C.c_int32 * B)(*[int(im.shape[1]) for im in images])
+    out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        L.check(L.load().mmcm_resize_crop_u8(flat.data_ptr(), offsets, heights, widths, B, int(size), out.data_ptr(),
+                                             _stream(flat)))
+    flat.record_stream(torch.cuda.current_stream(device))
+    return out
 
 
 def preprocess_u8(images_hwc: torch.Tensor, mean: Sequence[float], std: Sequence[float]) -> torch.Tensor:

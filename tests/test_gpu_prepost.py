@@ -144,3 +144,73 @@ def test_forward_u8_is_bit_identical_to_transform_then_forward(name):
     with pytest.raises(ValueError, match="std"):
         m.forward_u8(dbatch["input_ids"], dbatch["attention_mask"], img.cuda(), dbatch["text_present"],
                      dbatch["image_present"], mean, [0.0, 1.0, 1.0])
+
+
+RESIZE_SHAPES = [(375, 500), (500, 375), (224, 224), (224, 300), (1080, 1920), (100, 80), (231, 517), (640, 427),
+                 (225, 224), (3000, 223), (449, 449), (450, 675), (7, 9), (2048, 1365)]
+
+
+def test_resize_crop_u8_is_byte_identical_to_pillow():
+    """mmcm_resize_crop_u8 == T.CenterCrop(224)(T.Resize(224, antialias=True)(PIL image)) (dataset.py:106-108) for a
+    ragged batch: down-, up- and no scaling, extreme aspect ratios, odd crop offsets (round-half-even)."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from mmcm_b200 import prepost
+    from oracle import prepost_oracle as orc
+    rng = np.random.default_rng(11)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in RESIZE_SHAPES]
+    imgs[0][:] = 255                                            # saturated image: rounding must not overflow 255
+    imgs[1][::2] = 0                                            # high-frequency stripes
+    tf = T.Compose([T.Resize(224, antialias=True), T.CenterCrop((224, 224))])
+    got = prepost.resize_crop_u8([torch.from_numpy(i) for i in imgs], 224, device="cuda:0").cpu().numpy()
+    for i, im in enumerate(imgs):
+        ref = np.asarray(tf(Image.fromarray(im)))
+        assert np.array_equal(got[i], ref), f"image {i} {im.shape}: max diff {np.abs(got[i].astype(int) - ref).max()}"
+        if im.shape[0] * im.shape[1] < 400 * 600:               # the numpy restatement is slow on the big ones
+            assert np.array_equal(orc.resize_center_crop(im, 224), ref)
+    # another crop size, CUDA inputs
+    tf96 = T.Compose([T.Resize(96, antialias=True), T.CenterCrop((96, 96))])
+    got96 = prepost.resize_crop_u8([torch.from_numpy(i).cuda() for i in imgs[:6]], 96).cpu().numpy()
+    for i in range(6):
+        assert np.array_equal(got96[i], np.asarray(tf96(Image.fromarray(imgs[i]))))
+
+
+def test_raw_images_to_logits_equals_the_reference_transform_then_forward():
+    """decoded images -> resize_crop_u8 -> forward_u8  ==  eval_tf on the CPU (PIL + torchvision) -> forward."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from conftest import build_case
+    from test_gpu_forward import _make_module
+    from mmcm_b200 import prepost, synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    rng = np.random.default_rng(12)
+    shapes = RESIZE_SHAPES[:8]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    eval_tf = T.Compose([T.Resize(224, antialias=True), T.CenterCrop((224, 224)), T.ToTensor(), T.Normalize(mean, std)])
+    px = torch.stack([eval_tf(Image.fromarray(i)) for i in imgs])
+    b = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, len(imgs), seed=71).items()}
+    ref = m(**dict(b, pixel_values=px.cuda()))["logits"]
+    crops = prepost.resize_crop_u8([torch.from_numpy(i) for i in imgs], 224, device="cuda:0")
+    got = m.forward_u8(b["input_ids"], b["attention_mask"], crops, b["text_present"], b["image_present"], mean, std)
+    assert torch.equal(got, ref)
+    # the same through BatchedScorer with a ragged list (two internal batches)
+    import mmcm_b200 as P
+    thr = [0.2, 0.35, 0.5, 0.8, 0.95]
+    scorer = P.BatchedScorer(m, ["racist", "sexist", "homophobe", "religion", "otherhate"], thr, mean, std, max_batch=5)
+    res = scorer.score(b["input_ids"].cpu(), b["attention_mask"].cpu(), [torch.from_numpy(i) for i in imgs])
+    assert torch.equal(res["probs"], prepost.postprocess(ref, torch.tensor(thr))["probs"])
+
+
+def test_resize_crop_u8_argument_errors():
+    from mmcm_b200 import prepost
+    with pytest.raises(ValueError):
+        prepost.resize_crop_u8([], 224)
+    with pytest.raises(ValueError):
+        prepost.resize_crop_u8([torch.zeros(4, 4, 3)], 224)
+    with pytest.raises(ValueError, match="bad geometry"):
+        prepost.resize_crop_u8([torch.zeros(4, 4, 3, dtype=torch.uint8), torch.zeros(0, 5, 3, dtype=torch.uint8)], 8,
+                               device="cuda:0")
+    with pytest.raises(ValueError, match="size"):
+        prepost.resize_crop_u8([torch.zeros(4, 4, 3, dtype=torch.uint8)], 4096, device="cuda:0")

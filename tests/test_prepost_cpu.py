@@ -49,3 +49,18 @@ def test_postprocess_requires_gpu():
         prepost.postprocess(torch.zeros(2, 5), torch.full((5,), 0.5))
     with pytest.raises(ValueError):
         prepost.preprocess_u8(torch.zeros(1, 224, 224, 3, dtype=torch.uint8), [0.5] * 3, [0.5] * 3)
+
+
+def test_resize_oracle_is_pinned_against_pillow():
+    """oracle.prepost_oracle.resize_center_crop (numpy restatement of Pillow's Resample.c + torchvision's size / crop
+    arithmetic) against Pillow + torchvision themselves, the libraries the reference's eval_tf calls."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms as T
+    from oracle import prepost_oracle as orc
+    rng = np.random.default_rng(5)
+    tf = T.Compose([T.Resize(224, antialias=True), T.CenterCrop((224, 224))])
+    for h, w in [(375, 500), (500, 375), (224, 224), (224, 300), (100, 80), (231, 517), (225, 224), (449, 449), (7, 9)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(orc.resize_center_crop(img, 224), np.asarray(tf(Image.fromarray(img)))), (h, w)
+    assert orc.center_crop_origin(299, 225, 224) == (38, 0) and orc.center_crop_origin(297, 224, 224) == (36, 0)

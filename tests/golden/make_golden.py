@@ -31,10 +31,14 @@ from mmcm_b200 import arch as A, synthetic as syn  # noqa: E402
 from transformers import (AutoModel, CLIPConfig, CLIPModel, CLIPTextModel, CLIPVisionModel,  # noqa: E402
                           SiglipConfig, SiglipModel)
 
-# adapter 1: no network -> random init from config
-CLIPModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(CLIPConfig()))
-CLIPTextModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(CLIPConfig().text_config))
-CLIPVisionModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(CLIPConfig().vision_config))
+# adapter 1: no network -> random init from config (the encoder name selects the vision patch size, like the hub would)
+def _clip_config(name):
+    return CLIPConfig(vision_config={"patch_size": 16}) if "patch16" in name else CLIPConfig()
+
+
+CLIPModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(_clip_config(name)))
+CLIPTextModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(_clip_config(name).text_config))
+CLIPVisionModel.from_pretrained = classmethod(lambda cls, name, **kw: cls(_clip_config(name).vision_config))
 AutoModel.from_pretrained = classmethod(
     lambda cls, name, **kw: SiglipModel(SiglipConfig(text_config={"vocab_size": 256000})))
 
@@ -47,6 +51,7 @@ CASES = {
     "clip_mtl_h256_hardened": ("mtl", A.CLIP_B32, dict(head_hidden_dim=256), 1, True, 8, 8),
     "clip_mtl_h0_hardened": ("mtl", A.CLIP_B32, dict(head_hidden_dim=None), 2, True, 9, 8),
     "siglip_fusion_hardened": ("fusion", A.SIGLIP2_B16, dict(backend="siglip"), 3, True, 10, 8),
+    "clip_b16_fusion_hardened": ("fusion", A.CLIP_B16, dict(backend="clip"), 4, True, 11, 8),
 }
 TASKS = ["racist", "sexist", "homophobe", "religion", "otherhate"]
 
@@ -56,7 +61,7 @@ def run_case(name):
     torch.manual_seed(0)
     feats = {}
     if kind == "fusion":
-        m = MultiModalFusionClassifier("x", num_labels=5, **kw).eval()
+        m = MultiModalFusionClassifier("clip-patch%d" % a.patch, num_labels=5, **kw).eval()
         spec = A.fusion_spec(a, 5, 512)
         gt, gi = m.backbone.get_text_features, m.backbone.get_image_features
 

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 def _make_module(kind, a, kw, sd):
     import mmcm_b200 as P
     from mmcm_b200 import arch as A
-    name = {A.BACKEND_CLIP: "openai/clip-vit-base-patch32", A.BACKEND_SIGLIP: "google/siglip2-base-patch16-224"}[a.backend]
+    name = {A.BACKEND_CLIP: "openai/clip-vit-base-patch%d" % a.patch,
+            A.BACKEND_SIGLIP: "google/siglip2-base-patch16-224"}[a.backend]
     if kind == "fusion":
         m = P.MultiModalFusionClassifier(name, num_labels=5, **kw)
     else:
@@ -332,3 +333,29 @@ def test_pooled_last_layer_is_bit_identical_to_all_rows(name, B, mb):
         assert torch.equal(m._engine.stage("text_pooled"), tp_all)
         assert torch.equal(m._engine.stage("vision_pooled"), vp_all)
         assert m._engine.last_launch_count() > n_all          # the gather kernels ran
+
+
+@pytest.mark.parametrize("hardened", [True, False])
+def test_clip_vit_b16_encoder_matches_oracle(hardened):
+    """`encoder_name="openai/clip-vit-base-patch16"` (any CLIP checkpoint name is legal in R/config/*.yaml): 16-pixel
+    patches, 197 vision tokens -> 256-key attention tiles, K = 768 patch GEMM, CLS-pooled last layer."""
+    import mmcm_b200 as P
+    from mmcm_b200 import arch as A, synthetic as syn
+    a = A.CLIP_B16
+    sd = syn.make_state_dict(A.fusion_spec(a, 5, 512), a, seed=21, hardened=hardened)
+    batch = syn.make_inputs(a, 9, seed=210, edge_rows=True)
+    with torch.no_grad():
+        ref = oracle_forward("fusion", a, sd, batch)
+    m = P.MultiModalFusionClassifier("openai/clip-vit-base-patch16", num_labels=5)
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda:0").eval()
+    dbatch = {k: v.to("cuda:0") for k, v in batch.items()}
+    logits = m(**dbatch)["logits"]
+    _gate(logits.cpu(), ref, hardened)
+    m.set_option("pooled_last_layer", 0)
+    assert torch.equal(m(**dbatch)["logits"], logits)
+    m.set_option("attention_impl", 1)                       # mma.sync attention for the 197-token tower
+    try:
+        _gate(m(**dbatch)["logits"].cpu(), ref, hardened)
+    finally:
+        m.set_option("attention_impl", 0)

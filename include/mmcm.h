@@ -153,6 +153,8 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  *                      final LN -- those ops are row-wise, so the logits are bit-identical and 6 % of the GEMM work
  *                      is skipped; 0 = all rows like the reference.  (SigLIP vision always runs all rows: its MAP
  *                      head reads every token.)
+ *   "host_chunk"       mmcm_forward_host / _host_u8: samples per H2D pipeline stage of the vision tower
+ *                      (0 = default: about 200 MB of pixels per stage)
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue" *   1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl" * 0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and

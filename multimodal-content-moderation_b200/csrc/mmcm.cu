@@ -511,6 +511,7 @@ struct mmcm_handle_s {
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
   int opt_graph_max_batch = 0;   // off by default: small batches are bound by the GPU-side kernel chain, not the host
   int opt_pairs_text = 0, opt_pairs_vis = 0;   // > 0: CTA pairs the text / vision GEMMs may occupy (two-stream SM split)
+  int opt_host_chunk = 0;     // mmcm_forward_host*: samples per H2D pipeline stage of the vision tower (0 = ~200 MB)
   int opt_pooled_last = 1;   // last layer: out_proj / MLP / final LN only for the one row per sample that is pooled (exact)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
@@ -1565,9 +1566,12 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   CK(cudaMemcpyAsync(e->d_tp, text_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_ip, image_present, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min((int)B, e->opt_micro_batch);
-  // the vision chunks double as the H2D pipeline stages (pixels are 602 KB/sample): keep them <= 256 samples so that
-  // the copy of chunk i+1 overlaps the towers of chunk i; the text tower does not wait for pixels at all
-  const int vcap = std::min(e->opt_micro_batch, 256);
+  // the vision chunks double as the H2D pipeline stages (fp32 pixels are 602 KB/sample): the copy of chunk i+1 overlaps
+  // the towers of chunk i; the text tower does not wait for pixels at all
+  // stage size: ~200 MB of pixels (measured on B=1024: fp32 pixels best at 342 samples per stage, 51.6 k vs 50.3 k at
+  // 256; uint8 pixels best unsplit, 53.4 k vs 49.9 k -- tools/e2e_sweep.py); option "host_chunk" overrides
+  const int auto_chunk = std::max<int64_t>(64, ((int64_t)200 << 20) / (int64_t)px_bytes);
+  const int vcap = std::min(e->opt_micro_batch, e->opt_host_chunk > 0 ? e->opt_host_chunk : auto_chunk);
   const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, vcap, g_num_sms) : std::min((int)B, vcap);
   e->last_chunk_text = ct; e->last_chunk_vis = cv;
   CKR(ensure_arenas(e, ct, cv));
@@ -1717,6 +1721,10 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
   else if (n == "pooled_last_layer") h->opt_pooled_last = value != 0;
+  else if (n == "host_chunk") {
+    if (value < 0 || value > 65536) return fail(MMCM_EINVAL, "host_chunk out of range");
+    h->opt_host_chunk = (int)value;
+  }
   else if (n == "pairs_text" || n == "pairs_vision") {
     if (value < 0 || value > 74) return fail(MMCM_EINVAL, "%s must be in [0, 74]", name);
     (n == "pairs_text" ? h->opt_pairs_text : h->opt_pairs_vis) = (int)value;

@@ -355,14 +355,19 @@ def main():
     roof = None
     if rank == 0:
         m.set_option("streams", 1)          # serialise so that the per-GEMM events time only the GEMM
+        m(**batch)                          # one untimed pass in this mode
         m.set_option("time_gemms", 1)
-        m(**batch)
-        torch.cuda.synchronize()
-        gms, gfl, gn = eng.gemm_time()
+        passes = []
+        for _ in range(3):                  # median of three passes: a single 19 ms forward is sensitive to clock dips
+            m(**batch)
+            torch.cuda.synchronize()
+            passes.append(eng.gemm_time())
+        gms, gfl, gn = sorted(passes)[1]
         m.set_option("time_gemms", 0)
         m.set_option("streams", args.streams)
         achieved = gfl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all encoder GEMMs of one step, CUDA events per launch)",
+        roof = {"bound": "tensor", "kernel": "gemm2_tcgen05_kernel (all encoder GEMMs of one step, CUDA events per launch, serialised pass, "
+                                                  "median of 3)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 # DRAM bytes per GEMM launch, mean over the 4 encoder GEMMs of a text layer at chunk 1024, from the
                 # `ncu --set full` capture profiles/r01_gemm_pair_ncu_full.txt (qkv 267 MB, out 351 MB, fc1 350 MB,

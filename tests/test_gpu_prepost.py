@@ -175,6 +175,22 @@ def test_resize_crop_u8_is_byte_identical_to_pillow():
         assert np.array_equal(got96[i], np.asarray(tf96(Image.fromarray(imgs[i]))))
 
 
+def test_resize_crop_u8_awkward_geometries():
+    """1-pixel sides, primes, 10x up / down scaling, both crop parities, two crop sizes -- against Pillow."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from mmcm_b200 import prepost
+    rng = np.random.default_rng(2026)
+    shapes = [(1, 1), (1, 37), (41, 1), (2, 3), (31, 33), (64, 64), (65, 64), (64, 67), (97, 211), (640, 61), (59, 600)]
+    shapes += [tuple(int(v) for v in rng.integers(3, 300, 2)) for _ in range(40)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    for size in (32, 56, 224):
+        tf = T.Compose([T.Resize(size, antialias=True), T.CenterCrop((size, size))])
+        got = prepost.resize_crop_u8([torch.from_numpy(i) for i in imgs], size, device="cuda:0").cpu().numpy()
+        for i, im in enumerate(imgs):
+            assert np.array_equal(got[i], np.asarray(tf(Image.fromarray(im)))), (im.shape, size)
+
+
 def test_raw_images_to_logits_equals_the_reference_transform_then_forward():
     """decoded images -> resize_crop_u8 -> forward_u8  ==  eval_tf on the CPU (PIL + torchvision) -> forward."""
     from PIL import Image

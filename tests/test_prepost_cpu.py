@@ -64,3 +64,21 @@ def test_resize_oracle_is_pinned_against_pillow():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(orc.resize_center_crop(img, 224), np.asarray(tf(Image.fromarray(img)))), (h, w)
     assert orc.center_crop_origin(299, 225, 224) == (38, 0) and orc.center_crop_origin(297, 224, 224) == (36, 0)
+
+
+def test_resize_oracle_random_geometries_against_pillow():
+    """Seeded sweep over awkward geometries (1-pixel sides, primes, near-square, 10x up / down scaling, both crop
+    parities) for two crop sizes: the restatement must equal Pillow + torchvision everywhere."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms as T
+    from oracle import prepost_oracle as orc
+    rng = np.random.default_rng(2026)
+    shapes = [(1, 1), (1, 37), (41, 1), (2, 3), (31, 33), (64, 64), (65, 64), (64, 67), (97, 211), (640, 61), (59, 600)]
+    shapes += [tuple(int(v) for v in rng.integers(3, 300, 2)) for _ in range(25)]
+    for size in (32, 56):
+        tf = T.Compose([T.Resize(size, antialias=True), T.CenterCrop((size, size))])
+        for h, w in shapes:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            ref = np.asarray(tf(Image.fromarray(img)))
+            assert np.array_equal(orc.resize_center_crop(img, size), ref), (h, w, size)

@@ -64,7 +64,10 @@ struct AttCfg {
   static constexpr int BUF_BYTES = ((2 * TPAD + QROWS) * ATT_LD * 2 + TPAD + 15) / 16 * 16;
   // long sequences (SigLIP vision, 196 tokens: 76 KB per item) keep ONE buffer so that two CTAs fit on an SM;
   // short ones double-buffer (the next item streams in while the current one is computed)
-  static constexpr int NBUF = (BUF_BYTES > 56 * 1024) ? 1 : 2;
+#ifndef MMCM_ATT_DB_LIMIT
+#define MMCM_ATT_DB_LIMIT (56 * 1024)
+#endif
+  static constexpr int NBUF = (BUF_BYTES > MMCM_ATT_DB_LIMIT) ? 1 : 2;
   static constexpr int SMEM_BYTES = NBUF * BUF_BYTES;
   static constexpr int QBLOCKS = (TPAD / 16 + QW - 1) / QW;
 };

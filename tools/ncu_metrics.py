@@ -23,3 +23,16 @@ for r in rows[2:]:
     for w in WANT:
         if w in d:
             print(f"   {w:70s} {d[w]:>16s} {units[hdr.index(w)]}")
+    for w in ("smsp__inst_executed.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"):
+        if w in d:
+            print(f"   {w:70s} {d[w]:>16s} {units[hdr.index(w)]}")
+    stalls = []
+    for k, v in d.items():
+        if "issue_stalled" in k and k.endswith("_per_warp_active.pct"):
+            try:
+                stalls.append((float(v.replace(",", "")), k))
+            except ValueError:
+                pass
+    for v, k in sorted(stalls, reverse=True)[:6]:
+        print(f"   stall {k.split('issue_stalled_')[1].replace('_per_warp_active.pct', ''):62s} {v:16.2f} % of warp-active cycles")

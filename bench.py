@@ -171,6 +171,9 @@ def main():
                     help="1 = library default: after the last layer's attention only the pooled row of each sample "
                          "runs out_proj / MLP / final LN (row-wise ops, bit-identical logits); 0 = all rows. The "
                          "other setting is reported under `extras`")
+    ap.add_argument("--ln-fold", type=int, default=1,
+                    help="1 = library default: LayerNorm folded into the residual / consumer GEMMs (no LN pass in the "
+                         "layers); 0 = separate normalisation pass. The other setting is reported under `extras`")
     ap.add_argument("--pairs-text", type=int, default=0, help="CTA pairs the text-tower GEMMs may occupy (0 = all 74)")
     ap.add_argument("--pairs-vision", type=int, default=0)
     ap.add_argument("--attention-impl", type=int, default=0, help="0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256")
@@ -234,6 +237,7 @@ def main():
     m.set_option("pdl", args.pdl)
     m.set_option("varlen_text", args.varlen)
     m.set_option("pooled_last_layer", args.pooled_last)
+    m.set_option("ln_fold", args.ln_fold)
     m.set_option("pairs_text", args.pairs_text)
     m.set_option("pairs_vision", args.pairs_vision)
     m.set_option("attention_impl", args.attention_impl)
@@ -301,6 +305,7 @@ def main():
                   "note_pooled_last_layer": "1 = only the pooled row of each sample (CLS / EOS / last token) runs the last "
                                             "layer's out_proj, LN2, MLP and final LN: those ops are row-wise, logits are "
                                             f"bit-identical; the headline `value` uses {args.pooled_last}"}
+        extras[f"value_ln_fold_{1 - args.ln_fold}"] = timed_variant("ln_fold", 1 - args.ln_fold, args.ln_fold)
         if a.backend == 0:
             extras[f"value_varlen_text_{1 - args.varlen}"] = timed_variant("varlen_text", 1 - args.varlen, args.varlen)
             extras["note"] = ("varlen_text=1 packs the causal CLIP text tower up to each sample's EOS row (bit-identical "
@@ -395,7 +400,7 @@ def main():
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB/step/GPU vs 126 MB)",
                            "micro_batch": args.micro_batch or "library default", "streams": args.streams, "pdl": args.pdl,
                            "numa_node_rank0": numa,
-                           "varlen_text": args.varlen, "pooled_last_layer": args.pooled_last,
+                           "varlen_text": args.varlen, "pooled_last_layer": args.pooled_last, "ln_fold": args.ln_fold,
                            "algorithmic_gflop_per_sample": flops["total"] / 1e9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu, "parity": parity, "extras": extras}

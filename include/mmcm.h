@@ -137,11 +137,14 @@ MMCM_API int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t
                    void* stream);
 /* Number of kernels this library launched during the last mmcm_forward on this handle. */
 MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
+/* Samples per internal pass (micro-batch) the last forward used for the text and the vision tower. */
+MMCM_API int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* vision_chunk_out);
 /* CUDA-event time (ms) of the GEMM launches of the last forward when profiling was enabled with
  * mmcm_set_option(h, "time_gemms", 1); also returns the FLOPs they EXECUTED (2*M*N*K with the live row count of
  * packed text chunks). Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
-/* Options (name -> meaning; * = process-wide rather than per handle):
+/* Options (name -> meaning).  Every option is per handle; h == NULL edits the defaults that the stand-alone kernels
+ * below use ("pdl", "tma_epilogue", "attention_impl" only):
  *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)
  *   "micro_batch"      upper bound on the samples per internal pass of a tower (default 1024)
  *   "auto_chunk"       1 = pick, per tower, the chunk <= micro_batch whose GEMM tile counts fill whole rounds of the
@@ -155,11 +158,15 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  *                      head reads every token.)
  *   "host_chunk"       mmcm_forward_host / _host_u8: samples per H2D pipeline stage of the vision tower
  *                      (0 = default: about 200 MB of pixels per stage)
+ *   "ln_fold"          1 = default: no LayerNorm pass inside the encoder layers -- the residual GEMMs (out_proj, fc2)
+ *                      leave a bf16 copy and per-row statistics of the updated rows, the qkv / fc1 GEMMs apply mean /
+ *                      rstd in their epilogue on folded weights (see mmcm_gemm_lnfold); 0 = separate normalisation pass
+ *                      in front of qkv / fc1 (always the case for gemm_impl 1 and 2)
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
- *   "tma_epilogue" *   1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
- *   "attention_impl" * 0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
+ *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
+ *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
  *                      for 128 < T <= 256, mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 256
- *   "pdl" *            1 = every kernel is launched with programmatic stream serialization (prologues overlap the
+ *   "pdl"              1 = every kernel is launched with programmatic stream serialization (prologues overlap the
  *                      previous kernel's tail)
  *   "graph_max_batch"  forwards with B <= this are replayed as one CUDA graph from the third call of a shape on
  *                      (default 0 = off: a B=1 forward is bound by its 177-kernel dependency chain on the GPU, 1.45 ms
@@ -185,6 +192,28 @@ MMCM_API const char* mmcm_version(void);
 MMCM_API int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K,
                    int32_t epilogue, int32_t act, void* out, const float* resid, const float* pos,
                    int32_t P, int32_t T, int32_t impl, void* stream);
+/* --- LayerNorm folded into the GEMMs (what the towers run; stand-alone for the parity tests) -----------------------
+ * The encoder's pre-LN blocks (HF/models/clip/modeling_clip.py:372-384) compute Linear(LayerNorm(x)).  LayerNorm is
+ * row-wise over the Linear's K dimension, so
+ *     LayerNorm(x) W^T + b = rstd * (x (W*gamma)^T - mean * colsum) + b',  colsum[n] = sum_k (W*gamma)[n,k],  b' = b + W beta
+ * mmcm_fold_ln        weights, once per load: w_out bf16 [N,K] = bf16(scale_n * W * gamma), colsum_out, bias_out fp32 [N]
+ *                     (scale_n = q_scale for the first q_rows rows: dh^-1/2 of the fused Q|K|V matrix).
+ * mmcm_gemm_resid_stats   x[M,N] += A[M,K] @ W[N,K]^T + bias in place (fp32), xb_out = bf16(x), stats_out =
+ *                     float2 [N/128][M]: (sum, sum of squares about the slab mean) of every 128-column slab of the
+ *                     updated row.  N % 256 == 0.  Replaces out_proj / fc2 + the read half of the LayerNorm pass.
+ * mmcm_prep_rows      the same by-products for rows no GEMM produced (embeddings); gamma != NULL first applies
+ *                     LayerNorm(gamma, beta) to x in place (CLIP pre_layrnorm).  D in {512, 768, 1024}.
+ * mmcm_gemm_lnfold    out bf16 [M,N] = act(rstd * (xb @ w_folded^T - mean * colsum) + bias_folded), mean / rstd from
+ *                     `stats` (K = 128 * slabs <= 1024).  Replaces LayerNorm + qkv / fc1.  act = 0 or MMCM_ACT_*. */
+MMCM_API int mmcm_fold_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
+                          int32_t q_rows, float q_scale, void* w_out, float* colsum_out, float* bias_out, void* stream);
+MMCM_API int mmcm_prep_rows(float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
+                            void* xb_out, float* stats_out, void* stream);
+MMCM_API int mmcm_gemm_resid_stats(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K,
+                                   float* x, void* xb_out, float* stats_out, void* stream);
+MMCM_API int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* colsum,
+                              const float* stats, int32_t M, int32_t N, int32_t K, float eps, int32_t act, void* out,
+                              void* stream);
 /* y = LayerNorm(x) over the last dim D (512 or 768); x fp32 [rows,D]; out_bf16 and/or out_f32 may be NULL. */
 MMCM_API int mmcm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
                    void* out_bf16, float* out_f32, void* stream);

@@ -91,7 +91,26 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr int EPI_TMA_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled, 1 KB aligned
 
-template <int BLOCK_N>
+// ---- LN fold ------------------------------------------------------------------------------------------
+// LayerNorm is row-wise over the K dimension of the GEMM that consumes it:
+//     LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * s) + b',   s[n] = sum_k (W*gamma)[n,k],  b' = b + W beta
+// so the separate LayerNorm pass (read x fp32, write bf16: 6 B per element, 10 % of the forward) can go:
+//   * the PRODUCER of x -- the residual GEMM (out_proj / fc2), EPI_RESID_STATS -- pulls its x tile in by TMA,
+//     adds acc + bias in place, stores it back by TMA together with a bf16 copy (the consumer's A operand) and leaves,
+//     per row and 128-column slab, (sum, M2 about the slab mean): thread == row, so no shuffles.
+//   * the CONSUMER -- qkv / fc1, EPI_LNFOLD_* -- multiplies the un-normalised bf16 rows by W*gamma and applies
+//     rstd / mean (merged from the slabs with Chan's formula, fixed order) in its epilogue: 2 FMAs per element.
+// DRAM per residual element: 4 (read x) + 4 (write x) + 2 (write bf16) = 10 B instead of 8 (L2 reduce-add) + 6 (LN).
+#ifndef MMCM_STATS_XBUFS
+#define MMCM_STATS_XBUFS 2    /* in-place x tiles (32 rows x 32 fp32, 4 KB) per epilogue warp */
+#endif
+#ifndef MMCM_STATS_STAGES
+#define MMCM_STATS_STAGES 4   /* operand ring of the EPI_RESID_STATS instantiation (the x tiles need the room) */
+#endif
+constexpr int EPI_X_TILE_BYTES = 32 * 128;    // fp32 32 x 32, 128B-swizzled
+constexpr int EPI_XB_TILE_BYTES = 32 * 64;    // bf16 32 x 32, 64B-swizzled
+
+template <int BLOCK_N, int EPI = EPI_BIAS_BF16>
 struct Gemm2Cfg {
   static constexpr int BLOCK_M = 256;           // per pair; 128 rows per CTA
   static constexpr int BLOCK_K = 64;
@@ -100,30 +119,37 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;
+  static constexpr bool kStats = (EPI == EPI_RESID_STATS);
+  static constexpr bool kFold = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16);
+  static constexpr int XBUFS = MMCM_STATS_XBUFS;
+  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4 * (kFold ? 2 : 1);   // fold: bias' then colsum
+  static constexpr int EPI_STAGE = kStats ? XBUFS * EPI_X_TILE_BYTES : EPI_TMA_STAGE_BYTES;
+  static constexpr int EPI_STAGE2 = kStats ? EPI_XB_TILE_BYTES : 0;
 #ifndef MMCM_PAIR_STAGES
 #define MMCM_PAIR_STAGES 5   /* 4 stages already saturate the TMA->UMMA loop (tools/mainloop_probe.cu) */
 #endif
 #ifndef MMCM_PAIR_REG_THREADS
 #define MMCM_PAIR_REG_THREADS 384   /* __launch_bounds__ thread count used only to cap registers per thread */
 #endif
-  static constexpr int STAGES = (BLOCK_N == 256) ? MMCM_PAIR_STAGES : MMCM_PAIR_STAGES + 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_TMA_STAGE_BYTES + EPI_BIAS_BYTES) + 1024;
+  static constexpr int STAGES = kStats ? MMCM_STATS_STAGES : ((BLOCK_N == 256) ? MMCM_PAIR_STAGES : MMCM_PAIR_STAGES + 2);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * (EPI_STAGE + EPI_STAGE2 + EPI_BIAS_BYTES) + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
+  static_assert(SMEM_BYTES <= 232448, "CTA shared memory over the 227 KB limit");
 };
 
 template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMCM_PAIR_REG_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_c, const EpiParams ep, const int M_host, const int N,
-                     const int K, const int tma_out) {
-  using C = Gemm2Cfg<BLOCK_N>;
+                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d,
+                     const EpiParams ep, const int M_host, const int N, const int K, const int tma_out) {
+  using C = Gemm2Cfg<BLOCK_N, EPI>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES];    // used in the leader only
   __shared__ __align__(8) uint64_t bar_empty[C::STAGES];   // one copy per CTA (multicast commit)
   __shared__ __align__(8) uint64_t bar_tfull[2];           // one copy per CTA (multicast commit)
   __shared__ __align__(8) uint64_t bar_tempty[2];          // used in the leader only: 2 x EPI_WARPS arrivals
+  __shared__ __align__(8) uint64_t bar_x[C::EPI_WARPS][4];  // EPI_RESID_STATS: x tile of epilogue warp e, buffer j, has landed
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5;
@@ -142,6 +168,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (tma_out) prefetch_tmap(&tmap_c);
+    if (C::kStats) prefetch_tmap(&tmap_d);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -152,6 +179,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_init(smem_u32(&bar_tfull[s]), 1);
       mbar_init(smem_u32(&bar_tempty[s]), 2 * C::EPI_WARPS);
     }
+    if (C::kStats)
+      for (int s = 0; s < C::EPI_WARPS * 4; ++s) mbar_init(smem_u32(&bar_x[0][0] + s), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -227,13 +256,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // ===================== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====================
     const int e = warp - 4;
     const int lg = e & 3, ch = e >> 2;
-    const uint32_t stage_smem = epi_base + e * EPI_TMA_STAGE_BYTES;   // 1 KB aligned (epi_base is, 4 KB per warp)
-    const uint32_t bias_smem = epi_base + C::EPI_WARPS * EPI_TMA_STAGE_BYTES + e * C::EPI_BIAS_BYTES;
+    const uint32_t stage_smem = epi_base + e * C::EPI_STAGE;   // 1 KB aligned (epi_base is, 4 / 8 / 12 KB per warp)
+    const uint32_t stage2_smem = epi_base + C::EPI_WARPS * C::EPI_STAGE + e * C::EPI_STAGE2;   // bf16 tile (kStats)
+    const uint32_t bias_smem = epi_base + C::EPI_WARPS * (C::EPI_STAGE + C::EPI_STAGE2) + e * C::EPI_BIAS_BYTES;
     const bool tma_path = tma_out != 0 && EPI != EPI_PATCH_F32;
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr bool kF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32);
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t xph = 0;   // kStats: phase bit per x buffer
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const int row_base = m_blk * C::BLOCK_M + (int)rank * 128 + lg * 32;
@@ -252,6 +283,52 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           sts128(bias_smem + j * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+          if (C::kFold) {   // column sums of W*gamma behind the folded bias
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.colsum + col_base) + j);
+            sts128(bias_smem + HALF_N * 4 + j * 16, __float_as_uint(cs.x), __float_as_uint(cs.y), __float_as_uint(cs.z),
+                   __float_as_uint(cs.w));
+          }
+        }
+        __syncwarp();
+      }
+      // LN fold, consumer side: this lane's row statistics, merged from the 128-column slabs in fixed order
+      float ln_rs = 0.f, ln_nm = 0.f;   // rstd and -mean * rstd; rows beyond M keep 0 -> they store the (finite) bias
+      if (C::kFold) {
+        const int row = row_base + lane;
+        if (row < M) {
+          const int ns = ep.ln_slabs;
+          float2 p[8];
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < ns) {
+              p[i] = __ldg(ep.stats + (size_t)i * ep.stats_pitch + row);
+              sum += p[i].x;
+            }
+          const float inv_d = 1.0f / (float)(ns * LN_SLAB);
+          const float mean = sum * inv_d;
+          float m2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < ns) {
+              const float d = p[i].x * (1.0f / LN_SLAB) - mean;
+              m2 += p[i].y + (float)LN_SLAB * d * d;
+            }
+          ln_rs = rsqrtf(m2 * inv_d + ep.ln_eps);
+          ln_nm = -mean * ln_rs;
+        }
+      }
+      // LN fold, producer side: pull the first x tiles of this warp in while the main loop runs
+      if (C::kStats) {
+        if (row_base < M && lane == 0) {
+          bulk_wait_read0();       // the previous tile's stores have finished reading the x tiles / the bf16 tile
+          fence_proxy_async();
+#pragma unroll
+          for (int j = 0; j < C::XBUFS; ++j) {
+            const uint32_t bar = smem_u32(&bar_x[e][j]);
+            mbar_expect_tx(bar, EPI_X_TILE_BYTES);
+            tma_load_2d(&tmap_c, bar, stage_smem + j * EPI_X_TILE_BYTES, col_base + j * 32, row_base);
+          }
         }
         __syncwarp();
       }
@@ -260,7 +337,87 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (e == 0 && lane == 0) { if (tile == pair) trace_stamp(ep, 4); trace_stamp(ep, 7); }
       const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BLOCK_N + ch * HALF_N);
       if (row_base < M) {
-        if (!kF32) {
+        if constexpr (C::kStats) {
+          // x_new = x + acc + bias in place (thread == row), bf16 copy, running (sum, M2) of this row's 128 columns
+          static_assert(!C::kStats || HALF_N == LN_SLAB, "EPI_RESID_STATS needs BLOCK_N == 256");
+          constexpr int NCH = HALF_N / 32;
+          float run_s = 0.f, run_m2 = 0.f;
+          const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int j = c % C::XBUFS;
+            const uint32_t xt = stage_smem + j * EPI_X_TILE_BYTES + lane * 128;
+            mbar_wait(smem_u32(&bar_x[e][j]), (xph >> j) & 1u);
+            xph ^= 1u << j;
+            uint32_t r[32];
+            tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            float cs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 xo = lds128(xt + ((i ^ sw) << 4));
+              const uint4 bb = lds128(bias_smem + c * 128 + i * 16);
+              const float v0 = (__uint_as_float(r[4 * i]) + __uint_as_float(bb.x)) + __uint_as_float(xo.x);
+              const float v1 = (__uint_as_float(r[4 * i + 1]) + __uint_as_float(bb.y)) + __uint_as_float(xo.y);
+              const float v2 = (__uint_as_float(r[4 * i + 2]) + __uint_as_float(bb.z)) + __uint_as_float(xo.z);
+              const float v3 = (__uint_as_float(r[4 * i + 3]) + __uint_as_float(bb.w)) + __uint_as_float(xo.w);
+              r[4 * i] = __float_as_uint(v0); r[4 * i + 1] = __float_as_uint(v1);
+              r[4 * i + 2] = __float_as_uint(v2); r[4 * i + 3] = __float_as_uint(v3);
+              cs += (v0 + v1) + (v2 + v3);
+            }
+            const float cm = cs * (1.0f / 32.0f);
+            float cq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = __uint_as_float(r[i]) - cm;
+              cq = fmaf(d, d, cq);
+            }
+            if (c == 0) { run_s = cs; run_m2 = cq; }
+            else {   // Chan: merge 32 new elements into the 32 c seen so far
+              const float n0 = 32.0f * c;
+              const float d = cm - run_s / n0;
+              run_m2 += cq + d * d * (n0 * 32.0f / (n0 + 32.0f));
+              run_s += cs;
+            }
+            // the previous chunk's stores have read their tiles: its x buffer can take the chunk XBUFS ahead of it
+            if (c >= 1) {
+              if (lane == 0) {
+                bulk_wait_read0();
+                const int cn = c - 1 + C::XBUFS;
+                if (cn < NCH) {
+                  const int jn = (c - 1) % C::XBUFS;
+                  const uint32_t bar = smem_u32(&bar_x[e][jn]);
+                  fence_proxy_async();
+                  mbar_expect_tx(bar, EPI_X_TILE_BYTES);
+                  tma_load_2d(&tmap_c, bar, stage_smem + jn * EPI_X_TILE_BYTES, col_base + cn * 32, row_base);
+                }
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sts128(xt + ((i ^ sw) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            {   // bf16 copy: 32 rows x 64 B, 64B swizzle (16-byte slot i of row r sits at slot i ^ ((r >> 1) & 3))
+              const uint32_t bt = stage2_smem + lane * 64;
+              const uint32_t sw2 = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                sts128(bt + ((i ^ sw2) << 4),
+                       pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
+                       pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                       pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                       pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, stage_smem + j * EPI_X_TILE_BYTES, col_base + c * 32, row_base);
+              tma_store_2d(&tmap_d, stage2_smem, col_base + c * 32, row_base);
+              bulk_commit();
+            }
+          }
+          const int row = row_base + lane;
+          if (row < M) ep.stats[(size_t)(col_base / LN_SLAB) * ep.stats_pitch + row] = make_float2(run_s, run_m2);
+        } else if (!kF32) {
 #pragma unroll 1
           for (int c = 0; c < HALF_N / 64; ++c) {
             const bool tr = (e == 0 && lane == 0 && tile == pair);
@@ -271,13 +428,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               tmem_ld32(t_row + (uint32_t)(c * 64), r);
               tmem_ld_wait();
               if (tr && c == 0) trace_stamp(ep, 11);
-              epi_pack_bf16<EPI>(ep, bias_smem + c * 256, r, &w[0]);
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256, r, &w[0], ln_rs, ln_nm, HALF_N * 4);
             }
             {
               uint32_t r[32];
               tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r);
               tmem_ld_wait();
-              epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16]);
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16], ln_rs, ln_nm, HALF_N * 4);
             }
             if (tr && c == 0) trace_stamp(ep, 14);
             if (tma_path) {

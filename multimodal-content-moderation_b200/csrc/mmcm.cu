@@ -68,7 +68,23 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 static int g_num_sms = kNumSMs;
-static int g_pair_limit = 0;   // > 0: cap the CTA pairs a GEMM launch may occupy (SM partitioning between the towers)
+
+// Launch options live in the handle (mmcm_set_option); every entry point that launches kernels installs its handle's
+// set for the calling thread, so two handles driven from two threads never see each other's settings.  The
+// stand-alone kernels (mmcm_gemm_bf16, mmcm_attention, ...) use the defaults, which mmcm_set_option(NULL, ...) edits.
+struct LaunchOpts {
+  bool pdl = true;            // programmatic dependent launch on every kernel
+  bool tma_epilogue = true;   // TMA tile-store / reduce-add epilogue of the pair GEMM
+  int attention_impl = 0;     // 0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256
+  int pair_limit = 0;         // > 0: cap the CTA pairs a GEMM launch may occupy (SM partitioning between the towers)
+};
+static LaunchOpts g_default_opts;
+static thread_local const LaunchOpts* t_opts = &g_default_opts;
+struct OptsScope {
+  const LaunchOpts* prev;
+  explicit OptsScope(const LaunchOpts* o) : prev(t_opts) { t_opts = o; }
+  ~OptsScope() { t_opts = prev; }
+};
 
 // cudaFuncSetAttribute is per device: remember which devices a given kernel instantiation was configured on
 struct AttrOnce {
@@ -85,7 +101,6 @@ struct AttrOnce {
 
 // ------------------------------------------------------------------------------------------------ launches
 // Every kernel goes through launch_k: cudaLaunchKernelEx with programmatic stream serialization (PDL), see common.cuh.
-static bool g_pdl = true;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -97,7 +112,7 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = t_opts->pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -143,20 +158,23 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, i
 struct TmapKey {
   const void* p;
   int64_t rows, K;
-  int box;   // operand maps: box rows; output maps: -1 (bf16 64x32 box) / -2 (fp32 32x32 box)
+  int box;   // operand maps: box rows; output maps: -1 (bf16 64x32 box) / -2 (fp32 32x32 box) / -3 (bf16 32x32 box, 64B swizzle)
   bool operator<(const TmapKey& o) const { return std::tie(p, rows, K, box) < std::tie(o.p, o.rows, o.K, o.box); }
 };
 
 // output tile map for the TMA-store epilogue: row-major [rows, ld] bf16 or fp32, box = 128 bytes x 32 rows, 128B swizzle
-static int make_out_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, bool f32) {
+static int make_out_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, int kind) {
+  const bool f32 = kind == -2;
   const int esz = f32 ? 4 : 2;
+  const int inner_bytes = kind == -3 ? 64 : 128;
   cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32u};
+  cuuint32_t box[2] = {(cuuint32_t)(inner_bytes / esz), 32u};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                         const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        kind == -3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MMCM_ECUDA, "cuTensorMapEncodeTiled(out) failed (%d) rows=%lld ld=%lld", (int)r,
                                      (long long)rows, (long long)ld);
   return MMCM_OK;
@@ -169,7 +187,7 @@ static int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, 
   auto it = g_tmaps.find(k);
   if (it == g_tmaps.end()) {
     CUtensorMap m;
-    if (box < 0) CKR(make_out_tmap(&m, ptr, rows, K, box == -2));
+    if (box < 0) CKR(make_out_tmap(&m, ptr, rows, K, box));
     else CKR(make_tmap(&m, ptr, rows, K, box, weight));
     if (g_tmaps.size() > 8192) g_tmaps.clear();
     it = g_tmaps.emplace(k, m).first;
@@ -224,27 +242,35 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
   return MMCM_OK;
 }
 
-static bool g_tma_epilogue = true;
 template <int BN, int EPI>
 static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, int M, int N, int K,
                           cudaStream_t st) {
-  using C = Gemm2Cfg<BN>;
+  using C = Gemm2Cfg<BN, EPI>;
   auto kern = gemm2_tcgen05_kernel<BN, EPI>;
   static AttrOnce once;
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
   int pairs = g_num_sms / 2;
-  if (g_pair_limit > 0 && g_pair_limit < pairs) pairs = g_pair_limit;
+  if (t_opts->pair_limit > 0 && t_opts->pair_limit < pairs) pairs = t_opts->pair_limit;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   // TMA-store epilogue: bf16 tile stores; fp32 residual GEMMs as an L2 reduce-add (needs resid == out or no resid);
   // rows / pitches must keep the 16-byte global alignment TMA wants.  Otherwise the per-thread store path is used.
-  constexpr bool f32 = (EPI == EPI_BIAS_RESID_F32);
-  int tma_out = g_tma_epilogue && EPI != EPI_PATCH_F32 && (ep.ldo * (f32 ? 4 : 2)) % 16 == 0 &&
-                (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
-  if (f32 && ep.resid && ep.resid != ep.out) tma_out = 0;
-  CUtensorMap tc = ta;
+  constexpr bool f32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_RESID_STATS);
+  const bool aligned = (ep.ldo * (f32 ? 4 : 2)) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  int tma_out = t_opts->tma_epilogue && EPI != EPI_PATCH_F32 && aligned;
+  if (EPI == EPI_BIAS_RESID_F32 && ep.resid && ep.resid != ep.out) tma_out = 0;
+  CUtensorMap tc = ta, td = ta;
+  if (EPI == EPI_RESID_STATS) {   // the x tile travels in and out by TMA, so does its bf16 copy: no per-thread path
+    if (!aligned || !ep.xb || !ep.stats || (ep.ldo * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(ep.xb) & 15) != 0)
+      return fail(MMCM_EINVAL, "gemm: EPI_RESID_STATS needs 16-byte aligned out / xb rows and a stats buffer");
+    tma_out = 1;
+    CKR(get_tmap(&td, ep.xb, M, ep.ldo, -3, false));
+  }
+  if ((EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16) &&
+      (!ep.stats || !ep.colsum || !ep.bias || ep.ln_slabs < 1 || ep.ln_slabs > 8 || ep.ln_slabs * LN_SLAB != K))
+    return fail(MMCM_EINVAL, "gemm: EPI_LNFOLD needs stats, colsum, bias and K == 128 * slabs <= 1024");
   if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
-  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
+  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, td, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -252,11 +278,17 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
 template <int EPI>
 static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, const EpiParams& ep, int impl,
                            cudaStream_t st) {
-  if (impl == 1) {
-    dim3 grid(N / 32, (M + 31) / 32);
-    CK(launch_k(gemm_simt_kernel<EPI>, dim3(grid), dim3(256), 0, st, A, W, ep, M, N, K));
-    CK(cudaGetLastError());
-    return MMCM_OK;
+  constexpr bool kPairOnly = EPI >= EPI_RESID_STATS;   // LN-fold epilogues exist in the CTA-pair kernel only
+  if constexpr (kPairOnly) {
+    if (impl != 0 || N % 256 != 0)
+      return fail(MMCM_EINVAL, "gemm: epilogue %d needs gemm_impl 0 and N %% 256 == 0 (got impl %d, N %d)", EPI, impl, N);
+  } else {
+    if (impl == 1) {
+      dim3 grid(N / 32, (M + 31) / 32);
+      CK(launch_k(gemm_simt_kernel<EPI>, dim3(grid), dim3(256), 0, st, A, W, ep, M, N, K));
+      CK(cudaGetLastError());
+      return MMCM_OK;
+    }
   }
   CKR(ensure_driver());
   const int BN = (N % 256 == 0) ? 256 : 128;
@@ -265,11 +297,14 @@ static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, co
   if (impl == 0) {  // CTA-pair kernel: every CTA stages half of the B tile
     CKR(get_tmap(&tb, W, N, K, BN / 2, true));
     if (BN == 256) return launch_tc_pair<256, EPI>(ta, tb, ep, M, N, K, st);
-    return launch_tc_pair<128, EPI>(ta, tb, ep, M, N, K, st);
+    if constexpr (!kPairOnly) return launch_tc_pair<128, EPI>(ta, tb, ep, M, N, K, st);
   }
-  CKR(get_tmap(&tb, W, N, K, BN, true));
-  if (BN == 256) return launch_tc<256, EPI>(ta, tb, ep, M, N, K, st);
-  return launch_tc<128, EPI>(ta, tb, ep, M, N, K, st);
+  if constexpr (!kPairOnly) {
+    CKR(get_tmap(&tb, W, N, K, BN, true));
+    if (BN == 256) return launch_tc<256, EPI>(ta, tb, ep, M, N, K, st);
+    return launch_tc<128, EPI>(ta, tb, ep, M, N, K, st);
+  }
+  return fail(MMCM_EINVAL, "gemm: unsupported epilogue / implementation combination");
 }
 
 static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int epi, const EpiParams& ep, int impl,
@@ -289,6 +324,9 @@ static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int ep
     case EPI_BIAS_ACT_BF16: r = launch_gemm_epi<EPI_BIAS_ACT_BF16>(A, W, M, N, K, ep, impl, st); break;
     case EPI_BIAS_RESID_F32: r = launch_gemm_epi<EPI_BIAS_RESID_F32>(A, W, M, N, K, ep, impl, st); break;
     case EPI_PATCH_F32: r = launch_gemm_epi<EPI_PATCH_F32>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_RESID_STATS: r = launch_gemm_epi<EPI_RESID_STATS>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_LNFOLD_BF16: r = launch_gemm_epi<EPI_LNFOLD_BF16>(A, W, M, N, K, ep, impl, st); break;
+    case EPI_LNFOLD_ACT_BF16: r = launch_gemm_epi<EPI_LNFOLD_ACT_BF16>(A, W, M, N, K, ep, impl, st); break;
     default: return fail(MMCM_EINVAL, "gemm: unknown epilogue %d", epi);
   }
   CKR(r);
@@ -314,6 +352,20 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
   else return fail(MMCM_EINVAL, "layernorm: unsupported width %d (512, 768, 1024)", D);
   CK(cudaGetLastError());
   if (stats) stats->launches++;
+  return MMCM_OK;
+}
+
+// LN fold entry of a tower: optional in-place LayerNorm (CLIP pre_layrnorm), then bf16 copy + slab statistics
+static int launch_prep_rows(float* x, const float* g, const float* b, float eps, int rows, int D, bf16* xb, float2* stats,
+                            int pitch, cudaStream_t st, LaunchStats* S, const int* rows_dev = nullptr) {
+  if (rows <= 0) return MMCM_OK;
+  const int blocks = (rows + 7) / 8;
+  if (D == 512) CK(launch_k(prep_rows_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, rows_dev, xb, stats, pitch));
+  else if (D == 768) CK(launch_k(prep_rows_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, rows_dev, xb, stats, pitch));
+  else if (D == 1024) CK(launch_k(prep_rows_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, rows_dev, xb, stats, pitch));
+  else return fail(MMCM_EINVAL, "prep_rows: unsupported width %d (512, 768, 1024)", D);
+  CK(cudaGetLastError());
+  if (S) S->launches++;
   return MMCM_OK;
 }
 
@@ -345,7 +397,7 @@ static long long* g_gemm_trace = nullptr;   // dev tool, see mmcm_debug_set_gemm
 // 50-token vision tower) and for 128 < T <= 256 (SigLIP vision), mma.sync kernel otherwise (77-token text: 90 vs
 // 98 us; packed text stays on it too although tcgen05 would be 2 % faster end to end, so that packed and dense text
 // run the SAME attention kernel and stay bit-identical); 1 = always mma.sync; 2 = tcgen05 whenever T <= 256
-static int g_attention_impl = 0;
+// (LaunchOpts::attention_impl)
 
 template <int KMAX>
 static int launch_attention_tc(const bf16* qkv, const uint8_t* kvalid, int B, int T, int heads, int causal, bf16* out,
@@ -385,8 +437,8 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
                             cudaStream_t st, LaunchStats* stats, const int* seq_start = nullptr,
                             const int* seq_len = nullptr) {
   if (B <= 0) return MMCM_OK;
-  const bool tc128 = T <= 128 && (g_attention_impl == 2 || (g_attention_impl == 0 && T <= 64 && !seq_start));
-  const bool tc256 = T > 128 && T <= 256 && !seq_start && g_attention_impl != 1;
+  const bool tc128 = T <= 128 && (t_opts->attention_impl == 2 || (t_opts->attention_impl == 0 && T <= 64 && !seq_start));
+  const bool tc256 = T > 128 && T <= 256 && !seq_start && t_opts->attention_impl != 1;
   if (tc128 || tc256) {
     if (tc128) CKR(launch_attention_tc<128>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
     else CKR(launch_attention_tc<256>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
@@ -414,13 +466,14 @@ struct Part {          // one rectangular piece of a state-dict tensor and where
   int64_t src_pitch;   // elements between consecutive source rows
   void* dst;
   int64_t dst_pitch;
-  int kind;            // 0 = fp32, 1 = bf16
+  int kind;            // 0 = fp32, 1 = bf16, 2 = fp32 into the fold staging block (dst = float offset into it)
   float scale;
 };
 struct Slot {
   int64_t numel = 0;
   std::vector<Part> parts;
   bool loaded = false;
+  bool fold = false;   // input of the LN fold (a staged Linear or a layer norm): loading it re-arms the fold
 };
 
 __global__ void copy2d_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t rows, int64_t cols,
@@ -435,9 +488,19 @@ __global__ void copy2d_kernel(const float* __restrict__ src, void* __restrict__ 
   }
 }
 
+// The layer norms are folded into the Linears that consume them (fold_ln_kernel): wqkv / w1 hold bf16(W * gamma),
+// bqkv / b1 the folded biases b + W beta, sqkv / s1 the column sums the LN-fold epilogue subtracts the mean with.
 struct LayerW {
   bf16 *wqkv, *wo, *w1, *w2;
-  float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+  float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *sqkv, *s1;
+};
+struct FoldJob {   // one fold_ln_kernel launch: staged fp32 W [N,K] and b [N] -> bf16 W*gamma, colsum, folded bias
+  int64_t w_off, b_off;
+  const float *gamma, *beta;
+  int N, K, q_rows;
+  float q_scale;
+  bf16* wout;
+  float *colsum, *bias_out;
 };
 struct TowerW {
   int D, H, L, F, act;
@@ -456,7 +519,10 @@ struct Arena {  // activations of one tower for one micro-batch
   // last layer on the pooled rows only (one row per sample): residual, attention output, LN2 output, MLP hidden
   float* xp = nullptr;
   bf16 *attp = nullptr, *hp = nullptr, *ffp = nullptr;
+  // LN fold: per-row (sum, M2) of every 128-column slab of x / xp, written by the producer of the rows
+  float2 *stats = nullptr, *statsp = nullptr;
   int64_t rows = 0;
+  int mb = 0;
 };
 
 struct mmcm_handle_s {
@@ -465,6 +531,15 @@ struct mmcm_handle_s {
   std::vector<void*> allocs;
   std::unordered_map<std::string, Slot> slots;
   bool finalized = false;
+  // LN fold inputs: fp32 copies of the q/k/v/fc1 weights and biases, alive only between the first mmcm_load_weight
+  // of such a tensor and the next mmcm_finalize_weights
+  float* stage32 = nullptr;
+  int64_t stage32_floats = 0;
+  std::vector<FoldJob> fold_jobs;
+  bool fold_pending = false;
+  float* upload_buf = nullptr;   // host -> device bounce buffer of mmcm_load_weight (freed by finalize)
+  int64_t upload_floats = 0;
+  LaunchOpts opts;
   // every buffer of the repacked weight set, in allocation order (a pure function of cfg): the packed weight file
   struct WBuf { void* ptr; size_t bytes; };
   std::vector<WBuf> wbufs;
@@ -515,6 +590,7 @@ struct mmcm_handle_s {
   int opt_pooled_last = 1;   // last layer: out_proj / MLP / final LN only for the one row per sample that is pooled (exact)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
+  int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
   int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
 };
@@ -555,6 +631,14 @@ static void reg2d(Eng* e, const std::string& key, int64_t numel, int64_t src_off
   s.parts.push_back(Part{src_off, rows, cols, src_pitch, dst, dst_pitch, kind, scale});
 }
 
+// fp32 staging of a fold input: `off` floats into e->stage32 (allocated lazily by mmcm_load_weight)
+static void reg_staged(Eng* e, const std::string& key, int64_t numel, int64_t off) {
+  Slot& s = e->slots[key];
+  s.numel = numel;
+  s.fold = true;
+  s.parts.push_back(Part{0, 1, numel, numel, reinterpret_cast<void*>(static_cast<intptr_t>(off)), numel, 2, 1.0f});
+}
+
 static int setup_tower(Eng* e, TowerW& t, const std::string& prefix, int D, int H, int L, int F, int act, float eps) {
   t.D = D; t.H = H; t.L = L; t.F = F; t.act = act; t.eps = eps;
   if (D != H * ATT_DH) return fail(MMCM_EINVAL, "tower %s: hidden %d != heads %d * 64", prefix.c_str(), D, H);
@@ -573,24 +657,34 @@ static int setup_tower(Eng* e, TowerW& t, const std::string& prefix, int D, int 
     CKR(dalloc(e, &w.b2, D));
     CKR(dalloc(e, &w.ln1g, D)); CKR(dalloc(e, &w.ln1b, D));
     CKR(dalloc(e, &w.ln2g, D)); CKR(dalloc(e, &w.ln2b, D));
+    CKR(dalloc(e, &w.sqkv, 3 * D));
+    CKR(dalloc(e, &w.s1, F));
     const std::string p = prefix + "encoder.layers." + std::to_string(i) + ".";
     const int64_t dd = (int64_t)D * D;
-    reg(e, p + "self_attn.q_proj.weight", dd, w.wqkv, 1, qs);
-    reg(e, p + "self_attn.k_proj.weight", dd, w.wqkv + dd, 1);
-    reg(e, p + "self_attn.v_proj.weight", dd, w.wqkv + 2 * dd, 1);
-    reg(e, p + "self_attn.q_proj.bias", D, w.bqkv, 0, qs);
-    reg(e, p + "self_attn.k_proj.bias", D, w.bqkv + D, 0);
-    reg(e, p + "self_attn.v_proj.bias", D, w.bqkv + 2 * D, 0);
+    // q/k/v_proj and fc1 consume a LayerNorm: staged in fp32, folded with its gamma / beta at finalize
+    const int64_t o_wqkv = e->stage32_floats, o_bqkv = o_wqkv + 3 * dd, o_w1 = o_bqkv + 3 * D, o_b1 = o_w1 + (int64_t)F * D;
+    e->stage32_floats = o_b1 + F;
+    reg_staged(e, p + "self_attn.q_proj.weight", dd, o_wqkv);
+    reg_staged(e, p + "self_attn.k_proj.weight", dd, o_wqkv + dd);
+    reg_staged(e, p + "self_attn.v_proj.weight", dd, o_wqkv + 2 * dd);
+    reg_staged(e, p + "self_attn.q_proj.bias", D, o_bqkv);
+    reg_staged(e, p + "self_attn.k_proj.bias", D, o_bqkv + D);
+    reg_staged(e, p + "self_attn.v_proj.bias", D, o_bqkv + 2 * D);
+    reg_staged(e, p + "mlp.fc1.weight", (int64_t)F * D, o_w1);
+    reg_staged(e, p + "mlp.fc1.bias", F, o_b1);
     reg(e, p + "self_attn.out_proj.weight", dd, w.wo, 1);
     reg(e, p + "self_attn.out_proj.bias", D, w.bo, 0);
     reg(e, p + "layer_norm1.weight", D, w.ln1g, 0);
     reg(e, p + "layer_norm1.bias", D, w.ln1b, 0);
     reg(e, p + "layer_norm2.weight", D, w.ln2g, 0);
     reg(e, p + "layer_norm2.bias", D, w.ln2b, 0);
-    reg(e, p + "mlp.fc1.weight", (int64_t)F * D, w.w1, 1);
-    reg(e, p + "mlp.fc1.bias", F, w.b1, 0);
+    for (const char* k : {"layer_norm1.weight", "layer_norm1.bias", "layer_norm2.weight", "layer_norm2.bias"})
+      e->slots[p + k].fold = true;
     reg(e, p + "mlp.fc2.weight", (int64_t)D * F, w.w2, 1);
     reg(e, p + "mlp.fc2.bias", D, w.b2, 0);
+    // dh^-1/2 = 0.125 goes into the q rows (exact: a power of two)
+    e->fold_jobs.push_back(FoldJob{o_wqkv, o_bqkv, w.ln1g, w.ln1b, 3 * D, D, D, qs, w.wqkv, w.sqkv, w.bqkv});
+    e->fold_jobs.push_back(FoldJob{o_w1, o_b1, w.ln2g, w.ln2b, F, D, 0, 1.0f, w.w1, w.s1, w.b1});
   }
   return MMCM_OK;
 }
@@ -752,10 +846,16 @@ static void free_arena(Eng* e, Arena& a) {
   dfree(e, a.x); dfree(e, a.h); dfree(e, a.qkv); dfree(e, a.att); dfree(e, a.ff); dfree(e, a.pool_row);
   dfree(e, a.seq_start); dfree(e, a.seq_len); dfree(e, a.rows_dev);
   dfree(e, a.xp); dfree(e, a.attp); dfree(e, a.hp); dfree(e, a.ffp);
+  dfree(e, a.stats); dfree(e, a.statsp);
   a = Arena();
 }
 static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) {
   a.rows = rows;
+  a.mb = mb;
+  CKR(dalloc(e, &a.stats, rows * (t.D / LN_SLAB)));
+  CKR(dalloc(e, &a.statsp, (int64_t)mb * (t.D / LN_SLAB)));
+  CK(cudaMemset(a.stats, 0, rows * (t.D / LN_SLAB) * sizeof(float2)));
+  CK(cudaMemset(a.statsp, 0, (int64_t)mb * (t.D / LN_SLAB) * sizeof(float2)));
   CKR(dalloc(e, &a.x, rows * t.D));
   CKR(dalloc(e, &a.h, rows * t.D));
   CKR(dalloc(e, &a.qkv, rows * 3 * t.D));
@@ -788,8 +888,16 @@ static int vis_tokens(const mmcm_config& c) {
   return G * G + (c.backend == MMCM_BACKEND_CLIP ? 1 : 0);
 }
 
+// Captured graphs bake device pointers: whenever a buffer they may reference is reallocated they must go.
+static void invalidate_graphs(Eng* e) {
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
+
 static int ensure_arenas(Eng* e, int mbt, int mbv) {
   const mmcm_config& c = e->cfg;
+  if (mbt > e->mb_text || mbv > e->mb_vis) invalidate_graphs(e);
   if (mbt > e->mb_text) {
     CK(cudaDeviceSynchronize());
     free_arena(e, e->at);
@@ -868,6 +976,7 @@ static int choose_chunk(const TowerW& t, int T, int B, int cap, int sms) {
 static int ensure_batch(Eng* e, int64_t B) {
   if (B <= e->cap_B) return MMCM_OK;
   CK(cudaDeviceSynchronize());
+  invalidate_graphs(e);
   dfree(e, e->pooled_t); dfree(e, e->pooled_v); dfree(e, e->feat_t); dfree(e, e->feat_v);
   int64_t cap = e->cap_B ? e->cap_B : 64;
   while (cap < B) cap *= 2;
@@ -883,53 +992,66 @@ static int ensure_batch(Eng* e, int64_t B) {
 // `pooled_last`: a.pool_row holds the one row per sample the caller reads after the last layer; the last layer then
 // runs out_proj / LN2 / MLP on those B rows only and leaves their residual in a.xp [B, D] (a.x keeps the last layer's
 // INPUT).  Row-wise ops on gathered rows give the same bits as on the full matrix.
+static bool use_ln_fold(const Eng* e, const TowerW& t) {
+  return e->opt_ln_fold && e->opt_gemm_impl == 0 && e->opts.tma_epilogue && t.D % 256 == 0 && t.D <= 1024;
+}
+
+// On entry with the LN fold on, a.h holds bf16(a.x) and a.stats the slab statistics of a.x (launch_prep_rows or the
+// previous layer's fc2); every layer keeps that invariant.  With it off a.h is scratch for the LayerNorm output.
 static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T, const uint8_t* kvalid, int causal,
                       cudaStream_t st, const int* packed_rows = nullptr, bool pooled_last = false) {
   LaunchStats* S = &e->stats;
   const int D = t.D, F = t.F, impl = e->opt_gemm_impl;
   const bool packed = packed_rows != nullptr;
+  const bool fold = use_ln_fold(e, t);
   const int* rdev = packed_rows;                             // live row count of a packed chunk (device side)
   const int* sstart = packed ? a.seq_start : nullptr;
   const int* slen = packed ? a.seq_len : nullptr;
+  // h @ W^T with the LayerNorm in front of it: normalised rows x folded weights, or raw bf16 rows + LN-fold epilogue
+  auto ln_linear = [&](const float* x, bf16* h, float2* stats, int pitch, const bf16* W, const float* bias,
+                       const float* colsum, int M, int N, bf16* out, int act, const int* mdev) -> int {
+    EpiParams ep{};
+    ep.bias = bias; ep.out = out; ep.ldo = N; ep.act = act; ep.m_dev = mdev;
+    if (fold) {
+      ep.stats = stats; ep.stats_pitch = pitch; ep.colsum = colsum; ep.ln_slabs = D / LN_SLAB; ep.ln_eps = t.eps;
+      return launch_gemm(h, W, M, N, D, act ? EPI_LNFOLD_ACT_BF16 : EPI_LNFOLD_BF16, ep, impl, st, S);
+    }
+    CKR(launch_layernorm(x, nullptr, nullptr, t.eps, M, D, nullptr, h, nullptr, st, S, mdev));   // affine part lives in W / bias
+    return launch_gemm(h, W, M, N, D, act ? EPI_BIAS_ACT_BF16 : EPI_BIAS_BF16, ep, impl, st, S);
+  };
+  // x += A @ W^T + b; with the fold also the bf16 copy and the slab statistics the next LN-consuming GEMM needs
+  auto resid_linear = [&](const bf16* A, const bf16* W, const float* bias, float* x, bf16* xb, float2* stats, int pitch,
+                          int M, int K, const int* mdev, bool want_stats) -> int {
+    EpiParams ep{};
+    ep.bias = bias; ep.out = x; ep.resid = x; ep.ldo = D; ep.m_dev = mdev;
+    if (fold && want_stats) {
+      ep.xb = xb; ep.stats = stats; ep.stats_pitch = pitch;
+      return launch_gemm(A, W, M, D, K, EPI_RESID_STATS, ep, impl, st, S);
+    }
+    return launch_gemm(A, W, M, D, K, EPI_BIAS_RESID_F32, ep, impl, st, S);
+  };
   for (int i = 0; i < t.L; ++i) {
     const LayerW& w = t.layers[i];
-    // h = LN1(x)                                               HF clip :372
-    CKR(launch_layernorm(a.x, w.ln1g, w.ln1b, t.eps, rows, D, nullptr, a.h, nullptr, st, S, rdev));
-    // qkv = h @ [Wq*s | Wk | Wv]^T + [bq*s | bk | bv]          HF clip :313-319
-    EpiParams ep{};
-    ep.bias = w.bqkv; ep.out = a.qkv; ep.ldo = 3 * D; ep.m_dev = rdev;
-    CKR(launch_gemm(a.h, w.wqkv, rows, 3 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
+    const bool last = i == t.L - 1;
+    // qkv = LN1(x) @ [Wq*s | Wk | Wv]^T + [bq*s | bk | bv]     HF clip :372, :313-319
+    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.wqkv, w.bqkv, w.sqkv, rows, 3 * D, a.qkv, ACT_NONE, rdev));
     // att = softmax(q k^T + mask) v                            HF clip :321-332
     CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S, sstart, slen));
-    if (pooled_last && i == t.L - 1) {
+    if (pooled_last && last) {
       CK(launch_k(gather_pool_rows_kernel, dim3((B + 7) / 8), dim3(256), 0, st, (const bf16*)a.att, (const float*)a.x,
                   (const int*)a.pool_row, B, D, a.attp, a.xp));
       CK(cudaGetLastError());
       S->launches++;
-      ep = EpiParams{};
-      ep.bias = w.bo; ep.out = a.xp; ep.resid = a.xp; ep.ldo = D;
-      CKR(launch_gemm(a.attp, w.wo, B, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
-      CKR(launch_layernorm(a.xp, w.ln2g, w.ln2b, t.eps, B, D, nullptr, a.hp, nullptr, st, S));
-      ep = EpiParams{};
-      ep.bias = w.b1; ep.out = a.ffp; ep.ldo = F; ep.act = t.act;
-      CKR(launch_gemm(a.hp, w.w1, B, F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
-      ep = EpiParams{};
-      ep.bias = w.b2; ep.out = a.xp; ep.resid = a.xp; ep.ldo = D;
-      CKR(launch_gemm(a.ffp, w.w2, B, D, F, EPI_BIAS_RESID_F32, ep, impl, st, S));
+      CKR(resid_linear(a.attp, w.wo, w.bo, a.xp, a.hp, a.statsp, a.mb, B, D, nullptr, true));
+      CKR(ln_linear(a.xp, a.hp, a.statsp, a.mb, w.w1, w.b1, w.s1, B, F, a.ffp, t.act, nullptr));
+      CKR(resid_linear(a.ffp, w.w2, w.b2, a.xp, nullptr, nullptr, 0, B, F, nullptr, false));   // the final LN reads x itself
       break;
     }
     // x = x + att @ Wo^T + bo                                  HF clip :334, :379
-    ep = EpiParams{};
-    ep.bias = w.bo; ep.out = a.x; ep.resid = a.x; ep.ldo = D; ep.m_dev = rdev;
-    CKR(launch_gemm(a.att, w.wo, rows, D, D, EPI_BIAS_RESID_F32, ep, impl, st, S));
-    // h = LN2(x); ff = act(h @ W1^T + b1); x = x + ff @ W2^T + b2      HF clip :381-384, :347-351
-    CKR(launch_layernorm(a.x, w.ln2g, w.ln2b, t.eps, rows, D, nullptr, a.h, nullptr, st, S, rdev));
-    ep = EpiParams{};
-    ep.bias = w.b1; ep.out = a.ff; ep.ldo = F; ep.act = t.act; ep.m_dev = rdev;
-    CKR(launch_gemm(a.h, w.w1, rows, F, D, EPI_BIAS_ACT_BF16, ep, impl, st, S));
-    ep = EpiParams{};
-    ep.bias = w.b2; ep.out = a.x; ep.resid = a.x; ep.ldo = D; ep.m_dev = rdev;
-    CKR(launch_gemm(a.ff, w.w2, rows, D, F, EPI_BIAS_RESID_F32, ep, impl, st, S));
+    CKR(resid_linear(a.att, w.wo, w.bo, a.x, a.h, a.stats, (int)a.rows, rows, D, rdev, true));
+    // ff = act(LN2(x) @ W1^T + b1); x = x + ff @ W2^T + b2     HF clip :381-384, :347-351
+    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.w1, w.b1, w.s1, rows, F, a.ff, t.act, rdev));
+    CKR(resid_linear(a.ff, w.w2, w.b2, a.x, a.h, a.stats, (int)a.rows, rows, F, rdev, !last));
   }
   return MMCM_OK;
 }
@@ -964,10 +1086,13 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
     else return fail(MMCM_EINVAL, "text hidden %d unsupported (512, 768)", t.D);
     e->stats.launches++;
   }
-  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_text : 0;
+  if (use_ln_fold(e, t))   // bf16 copy + slab statistics of the embedded rows: what layer 0's QKV GEMM consumes
+    CKR(launch_prep_rows(a.x, nullptr, nullptr, t.eps, rows, t.D, a.h, a.stats, (int)a.rows, st, &e->stats,
+                         packed ? rows_slot : nullptr));
+  e->opts.pair_limit = e->opt_streams >= 2 ? e->opt_pairs_text : 0;
   const bool pl = e->opt_pooled_last && S > 1;
   const int rl = run_layers(e, t, a, rows, n, S, e->key_valid, clip ? 1 : 0, st, packed ? rows_slot : nullptr, pl);
-  g_pair_limit = 0;
+  e->opts.pair_limit = 0;
   CKR(rl);
   // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
   if (pl) CKR(launch_layernorm(a.xp, e->tfin_g, e->tfin_b, t.eps, n, t.D, nullptr, nullptr, pooled, st, &e->stats));
@@ -1019,17 +1144,21 @@ static int run_vision(Eng* e, const Pixels& px, int n, float* pooled, cudaStream
     CK(launch_k(cls_rows_kernel, dim3((n * D + 255) / 256), dim3(256), 0, st, e->cls_emb, e->vpos_emb, a.x, n, T, D));
     CK(cudaGetLastError());
     S->launches++;
-    CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
   }
+  if (use_ln_fold(e, t))   // pre_layrnorm (CLIP, in place) fused with the bf16 copy + slab statistics layer 0 consumes
+    CKR(launch_prep_rows(a.x, clip ? e->pre_g : nullptr, clip ? e->pre_b : nullptr, t.eps, rows, D, a.h, a.stats,
+                         (int)a.rows, st, S));
+  else if (clip)
+    CKR(launch_layernorm(a.x, e->pre_g, e->pre_b, t.eps, rows, D, nullptr, nullptr, a.x, st, S));  // pre_layrnorm
   if (clip) {   // pooled row = CLS (row 0 of each sample)
     CK(launch_k(fill_pool_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a.pool_row, n, T, 0));
     CK(cudaGetLastError());
     S->launches++;
   }
   const bool pl = clip && e->opt_pooled_last;   // the SigLIP MAP head reads every token of the last layer
-  g_pair_limit = e->opt_streams >= 2 ? e->opt_pairs_vis : 0;
+  e->opts.pair_limit = e->opt_streams >= 2 ? e->opt_pairs_vis : 0;
   const int rl = run_layers(e, t, a, rows, n, T, nullptr, 0, st, nullptr, pl);
-  g_pair_limit = 0;
+  e->opts.pair_limit = 0;
   CKR(rl);
   if (clip) {
     if (pl) CKR(launch_layernorm(a.xp, e->post_g, e->post_b, t.eps, n, D, nullptr, nullptr, pooled, st, S));
@@ -1109,9 +1238,7 @@ static int ensure_static_io(Eng* e, int64_t B) {
   CKR(dalloc(e, &e->d_tp, cap)); CKR(dalloc(e, &e->d_ip, cap));
   CKR(dalloc(e, &e->d_logits, cap * c.num_outputs)); CKR(dalloc(e, &e->d_probs, cap * c.num_outputs));
   e->host_cap = cap; e->host_S = c.max_pos;
-  // graphs captured earlier point into the freed buffers
-  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  e->graphs.clear();
+  invalidate_graphs(e);   // graphs captured earlier point into the freed buffers
   return MMCM_OK;
 }
 
@@ -1163,7 +1290,7 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
 extern "C" {
 
 const char* mmcm_last_error(void) { return g_err; }
-const char* mmcm_version(void) { return "mmcm-b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
+const char* mmcm_version(void) { return "mmcm-b200 0.2 (sm_100a; tcgen05/TMEM/TMA)"; }
 
 int mmcm_create(const mmcm_config* cfg, int device, mmcm_handle* out) {
   if (!cfg || !out) return fail(MMCM_EINVAL, "null argument");
@@ -1217,6 +1344,8 @@ int mmcm_destroy(mmcm_handle h) {
   clear_gemm_events(h->stats);
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->stage32) cudaFree(h->stage32);
+  if (h->upload_buf) cudaFree(h->upload_buf);
   {  // cached tensor maps may point into freed memory that a later allocation re-uses with another shape
     std::lock_guard<std::mutex> lk(g_mu);
     g_tmaps.clear();
@@ -1253,32 +1382,51 @@ int mmcm_load_weight(mmcm_handle h, const char* key, const float* src, int64_t n
   if (numel != s.numel)
     return fail(MMCM_EINVAL, "size mismatch for '%s': got %lld elements, expected %lld", key, (long long)numel,
                 (long long)s.numel);
-  // stage on the device (src may be host or device memory), then scatter/convert the pieces
+  // LN-fold inputs go to an fp32 staging block that lives until the next finalize.  If it is gone (a tensor is being
+  // replaced after a finalize) it comes back empty, and every staged tensor has to be pushed again before the fold
+  // can be redone -- mmcm_finalize_weights reports what is missing.
+  if (s.fold) {
+    if (!h->stage32) {
+      cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&h->stage32), (size_t)h->stage32_floats * 4);
+      if (ce != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc of the fold staging block failed: %s", cudaGetErrorString(ce));
+      for (auto& kv : h->slots)
+        for (const Part& p : kv.second.parts)
+          if (p.kind == 2) { kv.second.loaded = false; break; }
+    }
+    h->fold_pending = true;
+  }
+  // the source may be host or device memory: host tensors pass through a grow-only device buffer of the handle
   const float* dsrc = src;
-  float* stage = nullptr;
   cudaPointerAttributes attr;
   cudaError_t pe = cudaPointerGetAttributes(&attr, src);
   const bool on_device = (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged));
   if (pe != cudaSuccess) cudaGetLastError();
   if (!on_device) {
-    cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&stage), (size_t)numel * 4);
-    if (ce != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc staging for '%s' failed: %s", key, cudaGetErrorString(ce));
-    ce = cudaMemcpy(stage, src, (size_t)numel * 4, cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) {
-      cudaFree(stage);
-      return fail(MMCM_ECUDA, "H2D copy of '%s' failed: %s", key, cudaGetErrorString(ce));
+    if (numel > h->upload_floats) {
+      CK(cudaDeviceSynchronize());
+      if (h->upload_buf) cudaFree(h->upload_buf);
+      h->upload_buf = nullptr;
+      h->upload_floats = 0;
+      cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&h->upload_buf), (size_t)numel * 4);
+      if (ce != cudaSuccess) return fail(MMCM_ECUDA, "cudaMalloc staging for '%s' failed: %s", key, cudaGetErrorString(ce));
+      h->upload_floats = numel;
     }
-    dsrc = stage;
+    // stream-ordered on the legacy stream behind the previous tensor's repack kernels, which read the same buffer
+    cudaError_t ce = cudaMemcpyAsync(h->upload_buf, src, (size_t)numel * 4, cudaMemcpyHostToDevice, nullptr);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(nullptr);   // pageable sources may be re-used by the caller at once
+    if (ce != cudaSuccess) return fail(MMCM_ECUDA, "H2D copy of '%s' failed: %s", key, cudaGetErrorString(ce));
+    dsrc = h->upload_buf;
   }
+  OptsScope scope(&h->opts);
   for (const Part& p : s.parts) {
     const int64_t total = p.rows * p.cols;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    CK(launch_k(copy2d_kernel, dim3(blocks), dim3(256), 0, nullptr, dsrc + p.src_off, p.dst, p.rows, p.cols, p.src_pitch, p.dst_pitch, p.kind, p.scale));
+    void* dst = p.kind == 2 ? static_cast<void*>(h->stage32 + reinterpret_cast<intptr_t>(p.dst)) : p.dst;
+    CK(launch_k(copy2d_kernel, dim3(blocks), dim3(256), 0, nullptr, dsrc + p.src_off, dst, p.rows, p.cols, p.src_pitch,
+                p.dst_pitch, p.kind == 1 ? 1 : 0, p.scale));
   }
-  cudaError_t ce = cudaDeviceSynchronize();
-  if (stage) cudaFree(stage);
-  if (ce != cudaSuccess) return fail(MMCM_ECUDA, "weight repack of '%s' failed: %s", key, cudaGetErrorString(ce));
+  CK(cudaGetLastError());   // no device sync per tensor: the repack kernels are stream ordered, finalize waits once
   s.loaded = true;
   h->finalized = false;
   return MMCM_OK;
@@ -1295,11 +1443,30 @@ int mmcm_finalize_weights(mmcm_handle h) {
       ++missing;
     }
   if (missing) return fail(MMCM_ESTATE, "%d weight tensor(s) missing, e.g. '%s'", missing, first.c_str());
+  OptsScope scope(&h->opts);
+  if (h->fold_pending) {
+    // LayerNorm gamma / beta into the Linears that consume them (rowwise.cuh fold_ln_kernel)
+    if (!h->stage32) return fail(MMCM_ESTATE, "internal: LN-fold inputs are gone");
+    for (const FoldJob& j : h->fold_jobs)
+      CK(launch_k(fold_ln_kernel, dim3((j.N + 7) / 8), dim3(256), 0, nullptr, (const float*)(h->stage32 + j.w_off),
+                  (const float*)(h->stage32 + j.b_off), j.gamma, j.beta, j.N, j.K, j.q_rows,
+                  j.q_scale, j.wout, j.colsum, j.bias_out));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->stage32);
+    h->stage32 = nullptr;
+    h->fold_pending = false;
+  }
   if (h->cfg.backend == MMCM_BACKEND_SIGLIP) {
     const int D = h->cfg.vis_hidden;
     CK(launch_k(probe_query_kernel, dim3((D + 7) / 8), dim3(256), 0, nullptr, h->map_inw, h->map_inb, h->map_probe, h->map_q, D, 1.0f / sqrtf((float)ATT_DH)));
     CK(cudaGetLastError());
-    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaDeviceSynchronize());
+  if (h->upload_buf) {
+    cudaFree(h->upload_buf);
+    h->upload_buf = nullptr;
+    h->upload_floats = 0;
   }
   h->finalized = true;
   return MMCM_OK;
@@ -1311,7 +1478,7 @@ int mmcm_finalize_weights(mmcm_handle h) {
 // fp32 master copy.  Layout: PackedHeader | sizes[n_bufs] | pad to 4096 | buffers, each 256-byte aligned, in the
 // handle's allocation order (a pure function of mmcm_config, which the header carries and the loader compares).
 struct PackedHeader {
-  char magic[8];            // "MMCMPK01"
+  char magic[8];            // "MMCMPK02" (02: layer norms folded into the qkv / fc1 operands, column sums stored)
   uint32_t header_bytes;    // sizeof(PackedHeader)
   uint32_t cfg_bytes;       // sizeof(mmcm_config)
   uint64_t n_bufs;
@@ -1320,7 +1487,7 @@ struct PackedHeader {
   uint64_t checksum;        // packed_checksum over the payload
   mmcm_config cfg;
 };
-static const char kPackedMagic[8] = {'M', 'M', 'C', 'M', 'P', 'K', '0', '1'};
+static const char kPackedMagic[8] = {'M', 'M', 'C', 'M', 'P', 'K', '0', '2'};
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static uint64_t packed_checksum(const unsigned char* p, size_t n, uint64_t h = 0x9E3779B97F4A7C15ull) {
@@ -1449,6 +1616,11 @@ int mmcm_load_packed(mmcm_handle h, const char* path) {
   munmap(const_cast<unsigned char*>(base), len);
   CKR(rc);
   for (auto& kv : h->slots) kv.second.loaded = true;
+  if (h->stage32) {   // a half-pushed state dict is superseded by the file (which holds the folded weights)
+    cudaFree(h->stage32);
+    h->stage32 = nullptr;
+  }
+  h->fold_pending = false;
   h->finalized = true;
   return MMCM_OK;
 }
@@ -1510,6 +1682,7 @@ int mmcm_forward(mmcm_handle h, const int64_t* input_ids, const int64_t* attenti
                  float* probs_out, void* stream) {
   CKR(check_forward_args(h, input_ids, pixel_values, text_present, image_present, B, S, logits_out));
   CK(cudaSetDevice(h->device));
+  OptsScope scope(&h->opts);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (B > 0 && B <= h->opt_graph_max_batch && !h->stats.time_gemms) {
     bool handled = false;
@@ -1540,6 +1713,7 @@ int mmcm_forward_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* atte
   Pixels px;
   CKR(make_u8_pixels(&px, pixels_u8, mean3, std3));
   CK(cudaSetDevice(h->device));
+  OptsScope scope(&h->opts);
   return forward_device(h, input_ids, attention_mask, px, text_present, image_present, B, S, logits_out, probs_out,
                         reinterpret_cast<cudaStream_t>(stream));
 }
@@ -1552,6 +1726,7 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
                              float* logits_out, float* probs_out, cudaStream_t st) {
   CK(cudaSetDevice(e->device));
   if (B == 0) return MMCM_OK;
+  OptsScope scope(&e->opts);
   const mmcm_config& c = e->cfg;
   const size_t px_bytes = hpx.bytes_per_sample(c);
   const char* hsrc = hpx.u8 ? reinterpret_cast<const char*>(hpx.u8) : reinterpret_cast<const char*>(hpx.f32);
@@ -1675,6 +1850,13 @@ int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity
 
 int64_t mmcm_last_launch_count(mmcm_handle h) { return h ? h->stats.launches : 0; }
 
+int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* vision_chunk_out) {
+  if (!h) return fail(MMCM_EINVAL, "null handle");
+  if (text_chunk_out) *text_chunk_out = h->last_chunk_text;
+  if (vision_chunk_out) *vision_chunk_out = h->last_chunk_vis;
+  return MMCM_OK;
+}
+
 int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
   if (!h) return fail(MMCM_EINVAL, "null handle");
   CK(cudaSetDevice(h->device));
@@ -1698,7 +1880,16 @@ int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* la
 }
 
 int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
-  if (!h || !name) return fail(MMCM_EINVAL, "null argument");
+  if (!name) return fail(MMCM_EINVAL, "null argument");
+  if (!h) {   // defaults of the stand-alone kernels (mmcm_gemm_bf16, mmcm_attention, ...): no handle to carry them
+    std::lock_guard<std::mutex> lk(g_mu);
+    const std::string d(name);
+    if (d == "pdl") g_default_opts.pdl = value != 0;
+    else if (d == "tma_epilogue") g_default_opts.tma_epilogue = value != 0;
+    else if (d == "attention_impl" && value >= 0 && value <= 2) g_default_opts.attention_impl = (int)value;
+    else return fail(MMCM_EINVAL, "option '%s' = %lld cannot be set without a handle", name, (long long)value);
+    return MMCM_OK;
+  }
   const std::string n(name);
   if (n == "time_gemms") h->stats.time_gemms = value != 0;
   else if (n == "gemm_impl") {
@@ -1711,12 +1902,13 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "streams") {
     if (value != 1 && value != 2) return fail(MMCM_EINVAL, "streams must be 1 or 2");
     h->opt_streams = (int)value;
-  } else if (n == "pdl") g_pdl = value != 0;                    // process-wide: programmatic dependent launch on/off
-  else if (n == "tma_epilogue") g_tma_epilogue = value != 0;    // process-wide: TMA store / reduce-add epilogue of the pair GEMM
-  else if (n == "attention_impl") {                             // process-wide
+  } else if (n == "pdl") h->opts.pdl = value != 0;
+  else if (n == "tma_epilogue") h->opts.tma_epilogue = value != 0;
+  else if (n == "attention_impl") {
     if (value < 0 || value > 2) return fail(MMCM_EINVAL, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05 for T <= 128)");
-    g_attention_impl = (int)value;
+    h->opts.attention_impl = (int)value;
   }
+  else if (n == "ln_fold") h->opt_ln_fold = value != 0;
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
@@ -1734,9 +1926,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     h->opt_graph_max_batch = (int)value;
   }
   else return fail(MMCM_EINVAL, "unknown option '%s'", name);
-  // captured graphs bake the launch sequence of the options they were recorded under
-  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  h->graphs.clear();
+  invalidate_graphs(h);   // captured graphs bake the launch sequence of the options they were recorded under
   return MMCM_OK;
 }
 
@@ -1757,6 +1947,49 @@ int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, i
   ep.trace = g_gemm_trace;
   return launch_gemm(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(W), M, N, K, epilogue, ep, impl,
                      reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+// ---- LN fold, stand-alone (parity tests drive the same launchers the towers use) ----------------------------------
+int mmcm_fold_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
+                 int32_t q_rows, float q_scale, void* w_out, float* colsum_out, float* bias_out, void* stream) {
+  if (!W || !b || !gamma || !beta || !w_out || !colsum_out || !bias_out) return fail(MMCM_EINVAL, "null pointer");
+  if (N <= 0 || K <= 0) return fail(MMCM_EINVAL, "bad shape");
+  CK(launch_k(fold_ln_kernel, dim3((N + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), W, b, gamma, beta, N, K,
+              q_rows, q_scale, reinterpret_cast<bf16*>(w_out), colsum_out, bias_out));
+  CK(cudaGetLastError());
+  return MMCM_OK;
+}
+
+int mmcm_prep_rows(float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D, void* xb_out,
+                   float* stats_out, void* stream) {
+  if (!x || !xb_out || !stats_out || (gamma && !beta)) return fail(MMCM_EINVAL, "null pointer");
+  return launch_prep_rows(x, gamma, beta, eps, rows, D, reinterpret_cast<bf16*>(xb_out),
+                          reinterpret_cast<float2*>(stats_out), rows, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_gemm_resid_stats(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, float* x,
+                          void* xb_out, float* stats_out, void* stream) {
+  if (!A || !W || !x || !xb_out || !stats_out) return fail(MMCM_EINVAL, "null pointer");
+  EpiParams ep{};
+  ep.bias = bias; ep.out = x; ep.resid = x; ep.ldo = N; ep.xb = xb_out;
+  ep.stats = reinterpret_cast<float2*>(stats_out); ep.stats_pitch = M;
+  ep.trace = g_gemm_trace;
+  return launch_gemm(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(W), M, N, K, EPI_RESID_STATS, ep, 0,
+                     reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* colsum,
+                     const float* stats, int32_t M, int32_t N, int32_t K, float eps, int32_t act, void* out,
+                     void* stream) {
+  if (!xb || !w_folded || !bias_folded || !colsum || !stats || !out) return fail(MMCM_EINVAL, "null pointer");
+  if (K % LN_SLAB != 0) return fail(MMCM_EINVAL, "gemm_lnfold: K must be a multiple of %d", LN_SLAB);
+  EpiParams ep{};
+  ep.bias = bias_folded; ep.out = out; ep.ldo = N; ep.act = act; ep.colsum = colsum;
+  ep.stats = reinterpret_cast<float2*>(const_cast<float*>(stats)); ep.stats_pitch = M; ep.ln_slabs = K / LN_SLAB;
+  ep.ln_eps = eps;
+  ep.trace = g_gemm_trace;
+  return launch_gemm(reinterpret_cast<const bf16*>(xb), reinterpret_cast<const bf16*>(w_folded), M, N, K,
+                     act ? EPI_LNFOLD_ACT_BF16 : EPI_LNFOLD_BF16, ep, 0, reinterpret_cast<cudaStream_t>(stream), nullptr);
 }
 
 int mmcm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,

@@ -49,7 +49,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c4 = lane + 32 * i;
-    const float4 g = __ldg(g4 + c4), bb = __ldg(b4 + c4);
+    // gamma == nullptr: plain normalisation -- the affine part is folded into the consuming GEMM's weights (fold_ln_kernel)
+    const float4 g = gamma ? __ldg(g4 + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 bb = gamma ? __ldg(b4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 y;
     y.x = (v[i].x - mean) * rstd * g.x + bb.x;
     y.y = (v[i].y - mean) * rstd * g.y + bb.y;
@@ -62,6 +64,96 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
       p.y = pack_bf16x2(y.z, y.w);
       reinterpret_cast<uint2*>(out_bf16 + (size_t)warp * D)[c4] = p;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LN fold, entry of a tower (gemm2_tcgen05.cuh "LN fold"): the first layer's LayerNorm has no residual GEMM in front
+// of it, so this kernel leaves what EPI_RESID_STATS leaves -- a bf16 copy of the rows and, per 128-column slab,
+// (sum, M2 about the slab mean).  Lane l of the warp holds columns 4l..4l+3 of every slab, so slab i is v[i] across
+// the warp.  gamma != nullptr: the rows are first LayerNorm-ed in place (CLIP's pre_layrnorm, HF clip :677).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, const float eps,
+                 const int rows_host, const int* __restrict__ rows_dev, __nv_bfloat16* __restrict__ xb,
+                 float2* __restrict__ stats, const int stats_pitch) {
+  constexpr int V = D / 128;
+  pdl_trigger();
+  pdl_wait();
+  const int rows = rows_dev ? min(__ldg(rows_dev), rows_host) : rows_host;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)warp * D);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  if (gamma) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c4 = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      v[i].x = (v[i].x - mean) * rstd * g.x + bb.x;
+      v[i].y = (v[i].y - mean) * rstd * g.y + bb.y;
+      v[i].z = (v[i].z - mean) * rstd * g.z + bb.z;
+      v[i].w = (v[i].w - mean) * rstd * g.w + bb.w;
+      xr[c4] = v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float s = warp_sum(v[i].x + v[i].y + v[i].z + v[i].w);
+    const float m = s * (1.0f / 128.0f);
+    const float a = v[i].x - m, b = v[i].y - m, c = v[i].z - m, d = v[i].w - m;
+    const float q = warp_sum(a * a + b * b + c * c + d * d);
+    if (lane == 0) stats[(size_t)i * stats_pitch + warp] = make_float2(s, q);
+    uint2 p;
+    p.x = pack_bf16x2(v[i].x, v[i].y);
+    p.y = pack_bf16x2(v[i].z, v[i].w);
+    reinterpret_cast<uint2*>(xb + (size_t)warp * D)[lane + 32 * i] = p;
+  }
+}
+
+// Weight side of the LN fold, run once per weight load (mmcm_finalize_weights): for output row n of a Linear that
+// consumes LayerNorm(x)
+//   Wout[n,k]   = bf16(scale_n * W[n,k] * gamma[k])        scale_n = dh^-1/2 for the q rows of the fused QKV matrix
+//   colsum[n]   = sum_k float(Wout[n,k])                    (of the ROUNDED operand: it must cancel what the MMA sums)
+//   bias_out[n] = scale_n * (b[n] + sum_k W[n,k] * beta[k])
+// One warp per n.
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const int N, const int K, const int q_rows, const float q_scale,
+               __nv_bfloat16* __restrict__ Wout, float* __restrict__ colsum, float* __restrict__ bias_out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float sc = n < q_rows ? q_scale : 1.0f;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(size_t)n * K + k];
+    const __nv_bfloat16 wg = __float2bfloat16_rn(sc * w * gamma[k]);
+    Wout[(size_t)n * K + k] = wg;
+    cs += __bfloat162float(wg);
+    bs = fmaf(w, beta[k], bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_out[n] = sc * (b[n] + bs);
   }
 }
 

@@ -234,6 +234,12 @@ class Engine:
     def last_launch_count(self) -> int:
         return int(self.lib.mmcm_last_launch_count(self._h))
 
+    def last_chunks(self):
+        """(text, vision) micro-batch sizes the last forward split the batch into."""
+        t, v = C.c_int32(0), C.c_int32(0)
+        L.check(self.lib.mmcm_last_chunks(self._h, C.byref(t), C.byref(v)))
+        return t.value, v.value
+
     def gemm_time(self):
         ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
         L.check(self.lib.mmcm_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))

@@ -47,12 +47,17 @@ _SIGS = {
     "mmcm_forward_host_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_get_stage": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "mmcm_last_launch_count": (C.c_int64, [_P]),
+    "mmcm_last_chunks": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mmcm_gemm_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mmcm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "mmcm_last_error": (C.c_char_p, []),
     "mmcm_version": (C.c_char_p, []),
     "mmcm_gemm_bf16": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P,
                                  C.c_int32, C.c_int32, C.c_int32, _P]),
+    "mmcm_fold_ln": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "mmcm_prep_rows": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
+    "mmcm_gemm_resid_stats": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "mmcm_gemm_lnfold": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),
     "mmcm_layernorm": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mmcm_cast_bf16": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),

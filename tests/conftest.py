@@ -37,6 +37,10 @@ GOLDEN_CASES = {
     "clip_mtl_h0_hardened": ("mtl", "CLIP_B32", dict(head_hidden_dim=None), 2, True, 9, 8),
     "siglip_fusion_hardened": ("fusion", "SIGLIP2_B16", dict(backend="siglip"), 3, True, 10, 8),
     "clip_b16_fusion_hardened": ("fusion", "CLIP_B16", dict(backend="clip"), 4, True, 11, 8),
+    # default random init: the official absolute gate (logits 2e-2, probabilities 5e-3, decisions) for every model
+    "clip_mtl_h256_default": ("mtl", "CLIP_B32", dict(head_hidden_dim=256), 1, False, 8, 8),
+    "clip_mtl_h0_default": ("mtl", "CLIP_B32", dict(head_hidden_dim=None), 2, False, 9, 8),
+    "siglip_fusion_default": ("fusion", "SIGLIP2_B16", dict(backend="siglip"), 3, False, 10, 8),
 }
 TASKS = ["racist", "sexist", "homophobe", "religion", "otherhate"]
 

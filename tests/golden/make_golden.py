@@ -52,6 +52,10 @@ CASES = {
     "clip_mtl_h0_hardened": ("mtl", A.CLIP_B32, dict(head_hidden_dim=None), 2, True, 9, 8),
     "siglip_fusion_hardened": ("fusion", A.SIGLIP2_B16, dict(backend="siglip"), 3, True, 10, 8),
     "clip_b16_fusion_hardened": ("fusion", A.CLIP_B16, dict(backend="clip"), 4, True, 11, 8),
+    # default random init = what BASELINE.json's absolute tolerances (2e-2 / 5e-3 / decisions) are calibrated for
+    "clip_mtl_h256_default": ("mtl", A.CLIP_B32, dict(head_hidden_dim=256), 1, False, 8, 8),
+    "clip_mtl_h0_default": ("mtl", A.CLIP_B32, dict(head_hidden_dim=None), 2, False, 9, 8),
+    "siglip_fusion_default": ("fusion", A.SIGLIP2_B16, dict(backend="siglip"), 3, False, 10, 8),
 }
 TASKS = ["racist", "sexist", "homophobe", "religion", "otherhate"]
 

@@ -26,7 +26,13 @@ def _rel_l2(x, ref):
     return (x - ref).norm().item() / max(ref.norm().item(), 1e-12)
 
 
-def _gate(logits, ref, hardened):
+# Hardened-init gate, as a fraction of the batch logit std (SURVEY 8d proposed 5 %; what this build measures is
+# 1.2-1.5 % for the Fusion / SigLIP heads and ~3 % for the MTL heads, whose per-task logits are a 512-term fp32 dot
+# product of bf16-encoder features with x4-scaled weights).  A regression that doubles the error fails.
+REL_GATE = {"fusion": 0.025, "mtl": 0.045}
+
+
+def _gate(logits, ref, hardened, kind="fusion"):
     """Official gate on default init (BASELINE.json north_star); relative gate on hardened init."""
     err = (logits - ref).abs().max().item()
     p, pr = torch.sigmoid(logits), torch.sigmoid(ref)
@@ -36,10 +42,11 @@ def _gate(logits, ref, hardened):
         far = (pr - 0.5).abs() > 1e-3
     else:
         spread = ref.std().item()
-        assert err <= 0.05 * spread, f"logit max-abs {err} vs 5% of std {spread}"
+        rel = REL_GATE[kind]
+        assert err <= rel * spread, f"logit max-abs {err} vs {100 * rel:.1f}% of std {spread}"
         # sigmoid is 1/4-Lipschitz: the probability gate follows from the logit gate
-        assert (p - pr).abs().max().item() <= 0.25 * 0.05 * spread
-        far = (pr - 0.5).abs() > 0.25 * 0.05 * spread
+        assert (p - pr).abs().max().item() <= 0.25 * rel * spread
+        far = (pr - 0.5).abs() > 0.25 * rel * spread
     assert ((p >= 0.5) == (pr >= 0.5))[far].all(), "thresholded decisions differ away from 0.5"
 
 
@@ -55,7 +62,7 @@ def test_forward_matches_reference_golden(name):
     logits = out["logits"].float().cpu()
     ref = torch.from_numpy(gold["logits"])
     hardened = GOLDEN_CASES[name][4]
-    _gate(logits, ref, hardened)
+    _gate(logits, ref, hardened, kind)
     if kind == "fusion":
         assert abs(out["loss"].item() - float(gold["loss"])) <= 0.05 * max(1.0, float(gold["loss"]))
     # stage-wise: pooled tower outputs / projected features, relative L2 (bf16 GEMM chain measures 4-8e-3)
@@ -84,7 +91,7 @@ def test_forward_matches_oracle_ragged_batches(name, B, mb, streams):
     m.set_option("micro_batch", mb)
     m.set_option("streams", streams)
     logits = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
-    _gate(logits, ref, True)
+    _gate(logits, ref, True, kind)
     # determinism / idempotence: the same call again gives bit-identical logits
     again = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
     assert torch.equal(logits, again)
@@ -247,7 +254,7 @@ def test_tiny_batches_and_short_sequences(B, S):
         got = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
         assert got.shape == (B, 5)
         err = (got - ref).abs().max().item()
-        assert err <= 0.05 * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # 5 % of the hardened logit spread
+        assert err <= REL_GATE["fusion"] * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # of the hardened logit spread
 
 
 def test_two_models_in_one_process_do_not_interfere():
@@ -359,3 +366,42 @@ def test_clip_vit_b16_encoder_matches_oracle(hardened):
         _gate(m(**dbatch)["logits"].cpu(), ref, hardened)
     finally:
         m.set_option("attention_impl", 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Oracle parity AT the BASELINE.json batch sizes (cfg 2: CLIP-MTL 256, cfg 3: SigLIP-Fusion 256, cfg 4 / bench:
+# CLIP-Fusion 1024).  Samples are independent, so the oracle only has to score a subset of the rows: a stride through
+# the batch plus the rows either side of every internal chunk boundary (wave tails, partially filled tiles, the last
+# row).  The remaining rows are covered by bit-identity: the same rows scored as a small batch must give the same
+# bits as inside the full batch.
+@pytest.mark.parametrize("model,B,hardened", [("clip_mtl_h256", 256, False), ("clip_mtl_h256", 256, True),
+                                              ("siglip_fusion", 256, False), ("siglip_fusion", 256, True),
+                                              ("clip_fusion", 1024, False), ("clip_fusion", 1024, True)])
+def test_oracle_parity_at_baseline_batch_sizes(model, B, hardened):
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(model + ("_hardened" if hardened else "_default"))
+    m = _make_module(kind, a, kw, sd)
+    batch = syn.make_inputs(a, B, seed=500 + B, edge_rows=True)
+    dbatch = {k: v.to("cuda:0") for k, v in batch.items()}
+    full = m(**dbatch)["logits"].cpu()
+    assert full.shape == (B, 5) and torch.isfinite(full).all()
+    eng = m._engine
+    ct, cv = eng.last_chunks()
+    rows = set(range(0, B, max(1, B // 48))) | {0, 1, B - 2, B - 1}
+    for c in (ct, cv):                                         # rows around every internal micro-batch boundary
+        for edge in range(c, B, c):
+            rows |= {edge - 1, edge, min(edge + 1, B - 1)}
+    idx = torch.tensor(sorted(r for r in rows if 0 <= r < B))
+    assert len(idx) <= 96
+    sub = {k: v[idx].contiguous() for k, v in batch.items()}
+    with torch.no_grad():
+        ref = oracle_forward(kind, a, sd, sub)
+    _gate(full[idx], ref, hardened, kind)
+    # the same rows as their own small batch: identical bits (row-wise arithmetic, no cross-sample op anywhere)
+    small = m(**{k: v.to("cuda:0") for k, v in sub.items()})["logits"].cpu()
+    assert torch.equal(small, full[idx])
+    # and a contiguous slice that straddles the first chunk boundary of each tower
+    lo = max(0, min(ct, cv, B - 40) - 20)
+    sl = slice(lo, lo + 40)
+    part = m(**{k: v[sl].contiguous() for k, v in dbatch.items()})["logits"].cpu()
+    assert torch.equal(part, full[sl])

@@ -108,6 +108,105 @@ def test_gemm_patch_epilogue(lib, impl):
     assert (o[:, 0] == 123.0).all()                # class rows are not touched by the GEMM
 
 
+# ---------------------------------------------------------------------------------------------- LN fold
+# LayerNorm(x) W^T + b computed as rstd * (bf16(x) (W*gamma)^T - mean * colsum) + b' (include/mmcm.h, "LayerNorm
+# folded into the GEMMs").  Reference: torch fp32 layer_norm + linear on the fp32 x.
+
+def _slab_stats_ref(x):
+    """float2 [D/128][rows]: (sum, M2 about the slab mean) of every 128-column slab."""
+    rows, D = x.shape
+    xs = x.double().view(rows, D // 128, 128)
+    s = xs.sum(-1)
+    m2 = ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)
+    return torch.stack([s, m2], -1).permute(1, 0, 2).contiguous()      # [slab, row, 2]
+
+
+@pytest.mark.parametrize("rows,D,affine", [(1, 512, False), (333, 512, False), (640, 768, True), (77, 1024, True)])
+def test_prep_rows(lib, rows, D, affine):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.7
+    gam = torch.randn(D, device="cuda", generator=g)
+    bet = torch.randn(D, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-5) if affine else x.clone()
+    xb = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    st = torch.empty(D // 128, rows, 2, device="cuda")
+    _check(lib.mmcm_prep_rows(x.data_ptr(), gam.data_ptr() if affine else None, bet.data_ptr() if affine else None,
+                              1e-5, rows, D, xb.data_ptr(), st.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 1e-4                         # in-place LayerNorm (or untouched rows)
+    assert torch.equal(xb, x.bfloat16())                               # bf16 copy of exactly the fp32 rows left in x
+    want = _slab_stats_ref(x)
+    assert (st.double() - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(9856, 512, 512), (6400, 768, 768), (777, 768, 3072), (300, 512, 2048),
+                                   (31, 1024, 1024), (1, 512, 512)])
+def test_gemm_resid_stats(lib, M, N, K):
+    """x += A W^T + b in place, plus the bf16 copy and the slab statistics of the UPDATED rows."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g) * 1.5 + 0.3
+    ref = x + A.float() @ W.float().t() + bias
+    # bit-identity with the plain residual epilogue (TMA reduce-add): same (acc + bias) + x in fp32
+    x2 = x.clone()
+    _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 2, 0, x2.data_ptr(), x2.data_ptr(),
+                              None, 0, 0, 0, _stream()))
+    xb = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
+    st = torch.full((N // 128, M, 2), -1.0, device="cuda")
+    _check(lib.mmcm_gemm_resid_stats(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, x.data_ptr(), xb.data_ptr(),
+                                     st.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 2e-3
+    assert torch.equal(x, x2)
+    assert torch.equal(xb, x.bfloat16())
+    want = _slab_stats_ref(x)
+    assert (st.double() - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(9856, 1536, 512, 0), (9856, 2048, 512, 1), (6400, 2304, 768, 0),
+                                       (1000, 3072, 768, 2), (40, 256, 1024, 1), (1, 1536, 512, 0)])
+def test_gemm_lnfold_matches_layernorm_linear(lib, M, N, K, act):
+    """fold_ln + prep_rows + gemm_lnfold == act(Linear(LayerNorm(x))) up to the bf16 rounding of the operands."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + act)
+    x = torch.randn(M, K, device="cuda", generator=g) * (0.5 + 2.0 * torch.rand(M, 1, device="cuda", generator=g)) \
+        + 0.5 * torch.randn(M, 1, device="cuda", generator=g)            # per-row scale and mean offsets
+    W = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    gam = 1 + 0.1 * torch.randn(K, device="cuda", generator=g)
+    bet = 0.1 * torch.randn(K, device="cuda", generator=g)
+    q_rows, qs = (N // 3, 0.125) if N % 3 == 0 else (0, 1.0)
+    wf = torch.empty(N, K, device="cuda", dtype=torch.bfloat16)
+    cs = torch.empty(N, device="cuda")
+    bf = torch.empty(N, device="cuda")
+    _check(lib.mmcm_fold_ln(W.data_ptr(), b.data_ptr(), gam.data_ptr(), bet.data_ptr(), N, K, q_rows, qs, wf.data_ptr(),
+                            cs.data_ptr(), bf.data_ptr(), _stream()))
+    xb = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    st = torch.empty(K // 128, M, 2, device="cuda")
+    _check(lib.mmcm_prep_rows(x.data_ptr(), None, None, 1e-5, M, K, xb.data_ptr(), st.data_ptr(), _stream()))
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _check(lib.mmcm_gemm_lnfold(xb.data_ptr(), wf.data_ptr(), bf.data_ptr(), cs.data_ptr(), st.data_ptr(), M, N, K, 1e-5,
+                                act, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    scale = torch.ones(N, device="cuda")
+    scale[:q_rows] = qs
+    # weight side is exact arithmetic on the rounded operand
+    assert torch.equal(wf, (W * gam[None] * scale[:, None]).bfloat16())
+    assert (cs - wf.float().sum(-1)).abs().max().item() < 1e-3
+    assert (bf - scale * (b + W @ bet)).abs().max().item() < 1e-4
+    pre = (torch.nn.functional.layer_norm(x, (K,), gam, bet, 1e-5) @ W.t() + b) * scale
+    ref = pre if act == 0 else (_quick_gelu(pre) if act == 1 else torch.nn.functional.gelu(pre, approximate="tanh"))
+    # operands rounded to bf16 (2^-9 each) over a K-term sum of O(1) normalised values: error ~ 2^-9 * |w|_2 * |xhat|_2
+    # / sqrt(K)-ish; the bound below is 4x what the un-folded path (bf16(LN(x)) @ bf16(W)) measures on the same data
+    err = (out.float() - ref).abs()
+    assert (err <= 2e-2 * ref.abs() + 4e-2).all(), f"max err {err.max().item()}"
+    h = torch.nn.functional.layer_norm(x, (K,), gam, bet, 1e-5).bfloat16().float()
+    base = ((h @ W.bfloat16().float().t() + b) * scale - pre).abs().max().item()      # the separate-pass design
+    if act == 0:
+        assert err.max().item() <= max(4 * base, 4e-2), f"fold {err.max().item()} vs separate pass {base}"
+
+
 def test_gemm_rejects_bad_shapes(lib):
     A = torch.zeros(4, 96, device="cuda", dtype=torch.bfloat16)
     W = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
@@ -154,10 +253,7 @@ def _ref_attention(qkv, B, T, H, causal, kvalid):
     (11, 8, 1, True), (33, 8, 0, True), (128, 4, 1, True), (250, 2, 0, True)])
 @pytest.mark.parametrize("impl", [1, 2])     # 1 = mma.sync kernel, 2 = tcgen05 kernel (T <= 128; falls back above)
 def test_attention(lib, T, H, causal, masked, impl):
-    import mmcm_b200 as P
-    from mmcm_b200 import arch as A
-    eng = P.Engine(A.CLIP_B32, A.HEAD_FUSION, 5)     # process-wide switch lives behind a handle's set_option
-    eng.set_option("attention_impl", impl)
+    _check(lib.mmcm_set_option(None, b"attention_impl", impl))     # defaults of the stand-alone kernels (no handle)
     B = 6
     D = H * 64
     g = torch.Generator(device="cuda").manual_seed(T * 13 + H)
@@ -179,5 +275,4 @@ def test_attention(lib, T, H, causal, masked, impl):
     assert (out.float() - ref).abs().max().item() < 3e-2
     if masked:
         assert (out.view(B, T, D)[0] == 0).all()
-    eng.set_option("attention_impl", 0)
-    eng.close()
+    _check(lib.mmcm_set_option(None, b"attention_impl", 0))

@@ -125,7 +125,8 @@ def oracle_logits(kind, a, sd, batch):
 
 
 def cpu_arm(kind, a, sd, batch_size, steps, warmup, seed=1234):
-    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample of the workload."""
+    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample of the workload.
+    Every forward is timed on its own and the MEDIAN is reported: single forwards on a shared host vary by +-30 %."""
     import torch
     from mmcm_b200 import synthetic as syn
     cores = os.cpu_count() or 1
@@ -133,12 +134,95 @@ def cpu_arm(kind, a, sd, batch_size, steps, warmup, seed=1234):
     batch = syn.make_inputs(a, batch_size, seed=seed)
     for _ in range(warmup):
         oracle_logits(kind, a, sd, batch)
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         out = oracle_logits(kind, a, sd, batch)
-    dt = time.perf_counter() - t0
-    return {"value": batch_size * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": torch.get_num_threads(),
-            "logits": out, "batch": batch}
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return {"value": batch_size / med, "ms_per_step": med * 1e3, "cores": torch.get_num_threads(),
+            "ms_min": min(times) * 1e3, "ms_max": max(times) * 1e3, "logits": out, "batch": batch}
+
+
+def gemm_traffic(model):
+    """Mean DRAM bytes per encoder-GEMM launch of this build, from the committed `ncu --set full` capture
+    (profiles/r02_gemm_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep of the bench's own forward)."""
+    path = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        e = t[model]
+        return e["mean_dram_bytes_per_gemm_launch"], f"profiles/r02_gemm_traffic.json ({e['source']})"
+    except Exception:
+        return None, "no ncu capture of this model in profiles/r02_gemm_traffic.json"
+
+
+def torch_gpu_comparator(model, a, batch, steps):
+    """Second baseline: the encoders the reference delegates to -- Hugging Face CLIP / SigLIP
+    modules, random init -- on the SAME GPU in bf16 through torch's library kernels (cuBLASLt GEMMs, SDPA attention).
+    The fusion / MTL head (0.04 % of the FLOPs) is not run, which favours the comparator.  Never part of the product."""
+    import torch
+    try:
+        from transformers import CLIPConfig, CLIPModel, SiglipConfig, SiglipModel
+        dev = batch["input_ids"].device
+        torch.manual_seed(0)
+        if a.backend == 0:
+            hf = CLIPModel(CLIPConfig(vision_config={"patch_size": a.patch}))
+        else:
+            hf = SiglipModel(SiglipConfig(text_config={"vocab_size": a.vocab}))
+        hf = hf.to(dev, torch.bfloat16).eval()
+        px = batch["pixel_values"].to(torch.bfloat16)
+        ids, mask = batch["input_ids"], batch["attention_mask"]
+
+        def fwd():
+            with torch.no_grad():
+                t = hf.get_text_features(input_ids=ids, attention_mask=mask)
+                v = hf.get_image_features(pixel_values=px)
+            return t, v
+        for _ in range(3):
+            fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = max(3, min(steps, 10))
+        e0.record()
+        for _ in range(k):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        del hf
+        torch.cuda.empty_cache()
+        import transformers
+        return {"value": ids.shape[0] / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": k,
+                "what": f"transformers {transformers.__version__} {'CLIPModel' if a.backend == 0 else 'SiglipModel'}"
+                        ".get_text_features + get_image_features, bf16, sdpa, torch "
+                        f"{torch.__version__} (library kernels; heads excluded); comparator only"}
+    except Exception as ex:   # the comparator must never break the bench line
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
+def h2d_probe(dev, world, nbytes=256 << 20, reps=6):
+    """Pinned host -> device copy bandwidth of this rank while ALL ranks copy at once (GB/s): the ceiling of the e2e
+    leg's fp32 pixel stream on this box.  Returns (this rank's GB/s, aggregate GB/s)."""
+    import torch
+    import torch.distributed as dist
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbs], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return gbs, t.item()
 
 
 def parity_gate(logits, ref):
@@ -196,15 +280,15 @@ def main():
         if rank != 0:
             return 0
         B = 32
-        steps = max(1, min(args.steps, 5))
-        r = cpu_arm(kind, a, sd, B, steps, 1)
+        steps = max(10, min(args.steps, 20))     # >= 10 forwards, median (a B=32 forward is 0.3-0.4 s on 16 cores)
+        r = cpu_arm(kind, a, sd, B, steps, 2)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "steps": steps, "warmup": 2, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "sample": f"batch {B} per step"},
                 "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                                 "sample": f"{steps} forwards of batch {B} (oracle/scoring_oracle.py, torch fp32, "
-                                           f"{r['cores']} threads)"},
+                                 "sample": f"median of {steps} forwards of batch {B} (oracle/scoring_oracle.py, torch "
+                                           f"fp32, {r['cores']} threads; min {r['ms_min']:.0f} / max {r['ms_max']:.0f} ms)"},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
@@ -280,6 +364,15 @@ def main():
     ms_total = ms.item()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
+    if os.environ.get("MMCM_NCU_RANGE"):     # profiling runs: ONE forward inside an NVTX range (ncu --nvtx-include "measure/")
+        m.set_option("streams", 1)
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("measure")
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        m.set_option("streams", args.streams)
 
     # ------------------------------------------------------------------ extras: the same steps with one option flipped
     def timed_variant(option, setting, restore):
@@ -355,6 +448,67 @@ def main():
                             "api": "mmcm_forward_host_u8 (uint8 HWC crops in; the eval transform's ToTensor + Normalize "
                                    "run inside the patch im2col, logits bit-identical to the fp32-pixel call)"}
 
+        # what the box can deliver to all GPUs at once: the ceiling of the fp32-pixel e2e leg above
+        mine, agg = h2d_probe(dev, world)
+        e2e["h2d_ceiling"] = {"pinned_h2d_gbs_this_rank": mine, "pinned_h2d_gbs_all_ranks": agg,
+                              "samples_per_s_bound": agg * 1e9 / (in_bytes / B),
+                              "note": "all ranks copy 256 MiB pinned buffers concurrently (CUDA events); bound = aggregate "
+                                      "bandwidth / input bytes per sample of the reference's fp32 pixel_values contract"}
+
+    # ------------------------------------------------------------------ BASELINE config 5: one 22.5 k-sample scoring job
+    if world > 1 and not args.no_e2e:
+        N5 = 22500                                     # README's MMHS150K test size (R/README.md:115), strong scaling
+        lo, hi = sharding.shard_range(N5, rank, world)
+        nloc = hi - lo
+        # every rank materialises only its own contiguous shard (device resident, like `value`)
+        shard = {k: v.to(dev) for k, v in syn.make_inputs(a, nloc, seed=5000 + rank).items()}
+        best = None
+        for mb5 in (1024, 704):                        # 22 500 / 8 = 2813 = 4 x 704 - 3: a micro-batch without a short tail
+            def job():
+                outs = [m(**{k: v[s0:s0 + mb5] for k, v in shard.items()})["logits"] for s0 in range(0, nloc, mb5)]
+                return sharding.gather_scores(torch.cat(outs, 0), N5)
+            job()
+            sync_all()
+            t0 = time.perf_counter()
+            e0.record()
+            scores = job()
+            e1.record()
+            sync_all()
+            wall = (time.perf_counter() - t0) * 1e3
+            t5 = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            if best is None or t5.item() < best[0]:
+                best = (t5.item(), mb5, tuple(scores.shape))
+        if extras is None:
+            extras = {}
+        one_gpu_ms = N5 / (value / world) * 1e3        # the same job at this run's per-GPU device-resident rate
+        extras["config5"] = {"samples": N5, "ms": best[0], "samples_per_s": N5 / (best[0] * 1e-3), "micro_batch": best[1],
+                             "gathered_shape": list(best[2]), "shard": [lo, hi],
+                             "efficiency_vs_one_gpu_rate": one_gpu_ms / world / best[0],
+                             "note": "strong scaling: contiguous shards of one 22 500-sample job (sharding.shard_range), "
+                                     "barrier -> gathered [N, C] scores on every rank, max over ranks of wall clock and "
+                                     "CUDA events; efficiency = (N / per-GPU rate of `value`) / n_gpus / measured time, "
+                                     "i.e. what the ragged tail of the last micro-batch and the gather cost"}
+        del shard
+
+    # ------------------------------------------------------------------ online path: one request per forward
+    if rank == 0 and not args.no_e2e:
+        one = {k: v[:1].contiguous() for k, v in batch.items()}
+        for _ in range(10):
+            m(**one)
+        torch.cuda.synchronize()
+        lat = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            m(**one)["logits"].cpu()                   # the callers' per-request D2H (inference.py:216)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        if extras is None:
+            extras = {}
+        extras["latency_b1_ms"] = sorted(lat)[len(lat) // 2]
+        extras["latency_b1_launches"] = eng.last_launch_count()
+        if world == 1:
+            extras["torch_gpu_bf16"] = torch_gpu_comparator(args.model, a, batch, args.steps)
+
     # ------------------------------------------------------------------ roofline of the dominant kernel family
     peaks = _peaks()
     roof = None
@@ -371,24 +525,34 @@ def main():
         m.set_option("time_gemms", 0)
         m.set_option("streams", args.streams)
         achieved = gfl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        traffic, traffic_src = gemm_traffic(args.model)
+        # FLOPs the forward EXECUTES per sample: encoder GEMMs as launched (pooled-rows-only last layer, live rows of
+        # packed text) + the attention core and the head, which no option skips
+        exec_per_sample = gfl / B + flops["attention"] + flops["head"]
         roof = {"bound": "tensor", "kernel": "gemm2_tcgen05_kernel (all encoder GEMMs of one step, CUDA events per launch, serialised pass, "
                                                   "median of 3)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                # DRAM bytes per GEMM launch, mean over the 4 encoder GEMMs of a text layer at chunk 1024, from the
-                # `ncu --set full` capture profiles/r01_gemm_pair_ncu_full.txt (qkv 267 MB, out 351 MB, fc1 350 MB,
-                # fc2 625 MB; algorithmic operand+result bytes of the same launches: 325, 403, 406, 728 MB)
-                "traffic": 398e6 if args.model.startswith("clip") else None, "peak_source": peaks["source"], "gemm_launches": gn, "gemm_ms_per_step": gms,
+                # DRAM bytes per GEMM launch (dram__bytes_read + dram__bytes_write, mean over the encoder GEMM launches
+                # of one forward) from the committed ncu --set full capture of THIS build; null if none was taken
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_gemm_launch": flops.get("gemm_bytes_per_sample", 0.0) * B / max(gn, 1) or None,
+                "peak_source": peaks["source"], "gemm_launches": gn, "gemm_ms_per_step": gms,
                 "gemm_flops_per_step": gfl,
+                "note": "LayerNorm runs inside these GEMM launches (ln_fold): their time includes the residual-stream "
+                        "read-modify-write and the bf16 copy that used to be a separate HBM-bound pass",
                 "model_algorithmic_tflops": value / world * flops["total"] / 1e12,
-                "model_frac_of_peak": value / world * flops["total"] / 1e12 / peaks["tflops"]}
+                "model_frac_of_peak": value / world * flops["total"] / 1e12 / peaks["tflops"],
+                "model_executed_tflops": value / world * exec_per_sample / 1e12,
+                "model_executed_frac_of_peak": value / world * exec_per_sample / 1e12 / peaks["tflops"]}
 
     # ------------------------------------------------------------------ CPU baseline + parity gate (rank 0, N=1)
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(kind, a, sd, 32, 3, 1)
+        r = cpu_arm(kind, a, sd, 32, 10, 2)
         cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-               "sample": "3 forwards of batch 32 (oracle/scoring_oracle.py = fp32 restatement of the reference, torch CPU)"}
+               "sample": "median of 10 forwards of batch 32 after 2 warm-ups (oracle/scoring_oracle.py = fp32 restatement "
+                         f"of the reference, torch CPU; min {r['ms_min']:.0f} / max {r['ms_max']:.0f} ms per forward)"}
         got = m(**{k: v.to(dev) for k, v in r["batch"].items()})["logits"].float().cpu()
         parity = parity_gate(got, r["logits"])
 

@@ -162,6 +162,9 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  *                      leave a bf16 copy and per-row statistics of the updated rows, the qkv / fc1 GEMMs apply mean /
  *                      rstd in their epilogue on folded weights (see mmcm_gemm_lnfold); 0 = separate normalisation pass
  *                      in front of qkv / fc1 (always the case for gemm_impl 1 and 2)
+ *   "head_cluster"     1 = default: for B <= 144 the fused head kernel runs as one thread-block cluster of 8 CTAs per
+ *                      8 samples, each CTA computing an eighth of every Linear's columns and sharing them through
+ *                      distributed shared memory (the B = 1 head: 341 -> ~45 us); bit-identical logits; 0 = one CTA
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
@@ -195,25 +198,27 @@ MMCM_API int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int
 /* --- LayerNorm folded into the GEMMs (what the towers run; stand-alone for the parity tests) -----------------------
  * The encoder's pre-LN blocks (HF/models/clip/modeling_clip.py:372-384) compute Linear(LayerNorm(x)).  LayerNorm is
  * row-wise over the Linear's K dimension, so
- *     LayerNorm(x) W^T + b = rstd * (x (W*gamma)^T - mean * colsum) + b',  colsum[n] = sum_k (W*gamma)[n,k],  b' = b + W beta
- * mmcm_fold_ln        weights, once per load: w_out bf16 [N,K] = bf16(scale_n * W * gamma), colsum_out, bias_out fp32 [N]
- *                     (scale_n = q_scale for the first q_rows rows: dh^-1/2 of the fused Q|K|V matrix).
+ *     LayerNorm(x) W^T + b = rstd * ((x - mean) (W*gamma)^T) + b' = rstd * (x W'^T) + b',   b' = b + W beta,
+ * where W' = W*gamma with every row centred (sum_k W'[n,k] = 0), so that x W'[n] = (x - mean(x)) W'[n] for any x.
+ * mmcm_fold_ln        weights, once per load: w_out bf16 [N,K] = bf16(scale_n * W * gamma - its row mean), bias_out fp32
+ *                     [N] = scale_n * (b + W beta); resid_out (may be NULL) = sum_k w_out[n,k], what bf16 rounding
+ *                     leaves of the zero row sum (scale_n = q_scale for the first q_rows rows: dh^-1/2 of the fused
+ *                     Q|K|V matrix).  K <= 1024.
  * mmcm_gemm_resid_stats   x[M,N] += A[M,K] @ W[N,K]^T + bias in place (fp32), xb_out = bf16(x), stats_out =
  *                     float2 [N/128][M]: (sum, sum of squares about the slab mean) of every 128-column slab of the
  *                     updated row.  N % 256 == 0.  Replaces out_proj / fc2 + the read half of the LayerNorm pass.
  * mmcm_prep_rows      the same by-products for rows no GEMM produced (embeddings); gamma != NULL first applies
  *                     LayerNorm(gamma, beta) to x in place (CLIP pre_layrnorm).  D in {512, 768, 1024}.
- * mmcm_gemm_lnfold    out bf16 [M,N] = act(rstd * (xb @ w_folded^T - mean * colsum) + bias_folded), mean / rstd from
- *                     `stats` (K = 128 * slabs <= 1024).  Replaces LayerNorm + qkv / fc1.  act = 0 or MMCM_ACT_*. */
+ * mmcm_gemm_lnfold    out bf16 [M,N] = act(rstd * (xb @ w_folded^T) + bias_folded), rstd from `stats`
+ *                     (K = 128 * slabs <= 1024).  Replaces LayerNorm + qkv / fc1.  act = 0 or MMCM_ACT_*. */
 MMCM_API int mmcm_fold_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
-                          int32_t q_rows, float q_scale, void* w_out, float* colsum_out, float* bias_out, void* stream);
+                          int32_t q_rows, float q_scale, void* w_out, float* resid_out, float* bias_out, void* stream);
 MMCM_API int mmcm_prep_rows(float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
                             void* xb_out, float* stats_out, void* stream);
 MMCM_API int mmcm_gemm_resid_stats(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K,
                                    float* x, void* xb_out, float* stats_out, void* stream);
-MMCM_API int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* colsum,
-                              const float* stats, int32_t M, int32_t N, int32_t K, float eps, int32_t act, void* out,
-                              void* stream);
+MMCM_API int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* stats,
+                              int32_t M, int32_t N, int32_t K, float eps, int32_t act, void* out, void* stream);
 /* y = LayerNorm(x) over the last dim D (512 or 768); x fp32 [rows,D]; out_bf16 and/or out_f32 may be NULL. */
 MMCM_API int mmcm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
                    void* out_bf16, float* out_f32, void* stream);

@@ -78,26 +78,52 @@ SIGLIP2_B16 = ArchCfg(
     vocab=256000, max_pos=64, eos_id=-1, image=224, patch=16, proj_dim=768,
 )
 
+# SigLIP v1 (google/siglip-base-patch16-224): same towers, SentencePiece vocabulary of 32 000
+# (HF/models/siglip/configuration_siglip.py:77 default)
+SIGLIP_B16 = ArchCfg(
+    backend=BACKEND_SIGLIP,
+    text=TowerCfg(768, 12, 12, 3072, 1e-6, ACT_GELU_TANH),
+    vision=TowerCfg(768, 12, 12, 3072, 1e-6, ACT_GELU_TANH),
+    vocab=32000, max_pos=64, eos_id=-1, image=224, patch=16, proj_dim=768,
+)
+
 _BY_NAME = {
     "openai/clip-vit-base-patch32": CLIP_B32,
     "openai/clip-vit-base-patch16": CLIP_B16,
     "google/siglip2-base-patch16-224": SIGLIP2_B16,
-    "google/siglip-base-patch16-224": SIGLIP2_B16,
+    "google/siglip-base-patch16-224": SIGLIP_B16,
+}
+
+# processor constants of the two families (CLIPImageProcessor / SiglipImageProcessor defaults): what
+# `img_processor.image_mean / image_std` hold in R/src/data/dataset.py:100-110
+IMAGE_NORM = {
+    BACKEND_CLIP: ((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
+    BACKEND_SIGLIP: ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
 }
 
 
+def register_arch(encoder_name: str, cfg: ArchCfg) -> None:
+    """Teach `resolve_arch` the shapes of another checkpoint name (any CLIP / SigLIP base-size variant)."""
+    _BY_NAME[encoder_name] = cfg
+
+
 def resolve_arch(encoder_name: str, backend: str) -> ArchCfg:
-    """Map the reference's `encoder_name` (R/config/*.yaml `model.encoder_name`) to shapes."""
-    if encoder_name in _BY_NAME:
-        cfg = _BY_NAME[encoder_name]
-    else:
-        low = encoder_name.lower()
-        if "siglip" in low:
-            cfg = SIGLIP2_B16
-        elif "patch16" in low:
-            cfg = CLIP_B16
-        else:
-            cfg = CLIP_B32
+    """Map the reference's `encoder_name` (R/config/*.yaml `model.encoder_name`) to shapes.
+
+    The reference gets the shapes from the hub checkpoint's config; offline there is no config to read, so only names
+    whose architecture is known are accepted.  A local fine-tune directory whose name ends in one of the known names
+    resolves to it; anything else raises instead of silently building the wrong model (use `register_arch`)."""
+    cfg = _BY_NAME.get(encoder_name)
+    if cfg is None:
+        tail = encoder_name.rstrip("/").lower()
+        for known, c in _BY_NAME.items():
+            if tail.endswith(known.split("/")[-1]):
+                cfg = c
+                break
+    if cfg is None:
+        raise ValueError(
+            f"unknown encoder_name {encoder_name!r}: known architectures are {sorted(_BY_NAME)}; "
+            "register others with mmcm_b200.arch.register_arch(name, ArchCfg(...))")
     want = BACKEND_CLIP if backend.lower() == "clip" else BACKEND_SIGLIP
     if cfg.backend != want:
         raise ValueError(
@@ -240,4 +266,19 @@ def algorithmic_flops_per_sample(a: ArchCfg, head: int, num_labels: int = 5, fus
             hd += 2.0 * num_labels * (fd * head_hidden_dim + head_hidden_dim)
         else:
             hd += 2.0 * num_labels * fd
-    return {"vision": vis, "text": txt, "head": hd, "total": vis + txt + hd}
+    # attention core (4 T^2 d per layer: QK^T and PV), part of `vision` / `text` above, listed on its own so that
+    # "executed" FLOPs can be rebuilt from the GEMM launches (bench.py)
+    attn = a.vision.layers * 4.0 * a.vis_tokens ** 2 * a.vision.hidden + a.text.layers * 4.0 * a.max_pos ** 2 * a.text.hidden
+    # operand + result bytes of the encoder GEMMs per sample as the kernels move them (bf16 activations, fp32 residual
+    # stream read + written, bf16 copy of it, weights not counted: they are shared by the whole batch)
+    def tower_bytes(t: TowerCfg, tokens: int) -> float:
+        d, f = t.hidden, t.ffn
+        qkv = 2 * d + 2 * 3 * d                 # read bf16 rows, write q|k|v
+        out = 2 * d + 4 * d + 4 * d + 2 * d     # read attention output, read + write fp32 x, write bf16 copy
+        fc1 = 2 * d + 2 * f
+        fc2 = 2 * f + 4 * d + 4 * d + 2 * d
+        return t.layers * tokens * float(qkv + out + fc1 + fc2)
+    gemm_bytes = tower_bytes(a.vision, a.vis_tokens) + tower_bytes(a.text, a.max_pos) + \
+        pt * (2.0 * 3 * a.patch * a.patch + 4.0 * a.vision.hidden)
+    return {"vision": vis, "text": txt, "head": hd, "total": vis + txt + hd, "attention": attn,
+            "gemm_bytes_per_sample": gemm_bytes}

@@ -72,8 +72,11 @@ struct AttCfg {
   static constexpr int QBLOCKS = (TPAD / 16 + QW - 1) / QW;
 };
 
+#ifndef MMCM_ATT_MINB
+#define MMCM_ATT_MINB 1   /* min resident CTAs per SM the register allocator must allow */
+#endif
 template <int TPAD, int QW>
-__global__ void __launch_bounds__(QW * 32)
+__global__ void __launch_bounds__(QW * 32, MMCM_ATT_MINB)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const uint8_t* __restrict__ key_valid, const int* __restrict__ seq_start,
                  const int* __restrict__ seq_len, const int T_fixed, const int D, const int causal,

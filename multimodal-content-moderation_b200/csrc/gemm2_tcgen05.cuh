@@ -88,24 +88,42 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr int EPI_TMA_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled, 1 KB aligned
+// Staging tiles per epilogue warp for the TMA-store epilogues.  With ONE tile every chunk waited for the previous
+// chunk's bulk store to finish READING the tile before it could be refilled: a store-latency bubble per chunk that made
+// the K = 512 GEMMs epilogue bound (ncu, profiles/r02_gemm_shapes.txt: text qkv / fc1 at 52 / 49 % tensor pipe, 7.6 k
+// cycles per tile for a 4.1 k-cycle main loop).  With two, chunk c fills tile c & 1 while the store of chunk c - 1
+// drains the other (cp.async.bulk.wait_group.read 1).  The room comes from the operand ring: 4 stages instead of 5
+// (4 already saturate the TMA -> UMMA loop, tools/mainloop_probe.cu).
+#ifndef MMCM_EPI_NSTG
+#define MMCM_EPI_NSTG 2
+#endif
 
 // ---- LN fold ------------------------------------------------------------------------------------------
 // LayerNorm is row-wise over the K dimension of the GEMM that consumes it:
-//     LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * s) + b',   s[n] = sum_k (W*gamma)[n,k],  b' = b + W beta
+//     LN(x) W^T + b = rstd * ((x - mean) (W*gamma)^T) + b' = rstd * (x W'^T) + b',   b' = b + W beta,
+//     W' = W*gamma with every ROW centred (sum_k W'[n,k] = 0, so x W'[n] = (x - mean(x)) W'[n] for any x)
 // so the separate LayerNorm pass (read x fp32, write bf16: 6 B per element, 10 % of the forward) can go:
 //   * the PRODUCER of x -- the residual GEMM (out_proj / fc2), EPI_RESID_STATS -- pulls its x tile in by TMA,
 //     adds acc + bias in place, stores it back by TMA together with a bf16 copy (the consumer's A operand) and leaves,
 //     per row and 128-column slab, (sum, M2 about the slab mean): thread == row, so no shuffles.
-//   * the CONSUMER -- qkv / fc1, EPI_LNFOLD_* -- multiplies the un-normalised bf16 rows by W*gamma and applies
-//     rstd / mean (merged from the slabs with Chan's formula, fixed order) in its epilogue: 2 FMAs per element.
+//   * the CONSUMER -- qkv / fc1, EPI_LNFOLD_* -- multiplies the un-normalised bf16 rows by W' and applies rstd
+//     (variance merged from the slabs with Chan's formula, fixed order) in its epilogue: one FMA per element, the
+//     same instruction and shared-memory traffic as the plain bias epilogue.  (A first version kept W*gamma
+//     un-centred and subtracted mean * colsum in the epilogue: the extra column-sum loads from shared memory, which
+//     the main loop already saturates, cost fc1 10 % -- tools/gemm_bench_fold.py.)
 // DRAM per residual element: 4 (read x) + 4 (write x) + 2 (write bf16) = 10 B instead of 8 (L2 reduce-add) + 6 (LN).
 #ifndef MMCM_STATS_XBUFS
 #define MMCM_STATS_XBUFS 2    /* in-place x tiles (32 rows x 32 fp32, 4 KB) per epilogue warp */
 #endif
 #ifndef MMCM_STATS_STAGES
 #define MMCM_STATS_STAGES 4   /* operand ring of the EPI_RESID_STATS instantiation (the x tiles need the room) */
+#endif
+#ifndef MMCM_STATS_EARLY
+#define MMCM_STATS_EARLY 0    /* 1: refill an x buffer at the top of the next chunk instead of in its middle */
 #endif
 constexpr int EPI_X_TILE_BYTES = 32 * 128;    // fp32 32 x 32, 128B-swizzled
 constexpr int EPI_XB_TILE_BYTES = 32 * 64;    // bf16 32 x 32, 64B-swizzled
@@ -122,11 +140,11 @@ struct Gemm2Cfg {
   static constexpr bool kStats = (EPI == EPI_RESID_STATS);
   static constexpr bool kFold = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16);
   static constexpr int XBUFS = MMCM_STATS_XBUFS;
-  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4 * (kFold ? 2 : 1);   // fold: bias' then colsum
-  static constexpr int EPI_STAGE = kStats ? XBUFS * EPI_X_TILE_BYTES : EPI_TMA_STAGE_BYTES;
+  static constexpr int EPI_BIAS_BYTES = (BLOCK_N / 2) * 4;
+  static constexpr int EPI_STAGE = kStats ? XBUFS * EPI_X_TILE_BYTES : MMCM_EPI_NSTG * EPI_TMA_STAGE_BYTES;
   static constexpr int EPI_STAGE2 = kStats ? EPI_XB_TILE_BYTES : 0;
 #ifndef MMCM_PAIR_STAGES
-#define MMCM_PAIR_STAGES 5   /* 4 stages already saturate the TMA->UMMA loop (tools/mainloop_probe.cu) */
+#define MMCM_PAIR_STAGES (MMCM_EPI_NSTG == 2 ? 4 : 5)   /* 4 stages already saturate the TMA->UMMA loop (tools/mainloop_probe.cu) */
 #endif
 #ifndef MMCM_PAIR_REG_THREADS
 #define MMCM_PAIR_REG_THREADS 384   /* __launch_bounds__ thread count used only to cap registers per thread */
@@ -265,6 +283,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     int as = 0;
     uint32_t aphase = 0;
     uint32_t xph = 0;   // kStats: phase bit per x buffer
+    uint32_t cc = 0;    // TMA-store epilogues: running chunk counter -> staging tile cc % MMCM_EPI_NSTG
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const int row_base = m_blk * C::BLOCK_M + (int)rank * 128 + lg * 32;
@@ -278,21 +297,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         if (row_base < M) epi_load_addend<EPI>(ep, lane, row_base, col_base, M, xa);
       } else {
+        // QuickGELU epilogues work on halved constants (epi_pack_bf16): exact, one instruction fewer per element
+        constexpr bool kActEpi = (EPI == EPI_BIAS_ACT_BF16 || EPI == EPI_LNFOLD_ACT_BF16);
+        const float hs = (kActEpi && ep.act == ACT_QUICK_GELU) ? 0.5f : 1.0f;
 #pragma unroll
         for (int j = lane; j < HALF_N / 4; j += 32) {
           const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          sts128(bias_smem + j * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
-          if (C::kFold) {   // column sums of W*gamma behind the folded bias
-            const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.colsum + col_base) + j);
-            sts128(bias_smem + HALF_N * 4 + j * 16, __float_as_uint(cs.x), __float_as_uint(cs.y), __float_as_uint(cs.z),
-                   __float_as_uint(cs.w));
-          }
+          sts128(bias_smem + j * 16, __float_as_uint(b.x * hs), __float_as_uint(b.y * hs), __float_as_uint(b.z * hs),
+                 __float_as_uint(b.w * hs));
         }
         __syncwarp();
       }
       // LN fold, consumer side: this lane's row statistics, merged from the 128-column slabs in fixed order
-      float ln_rs = 0.f, ln_nm = 0.f;   // rstd and -mean * rstd; rows beyond M keep 0 -> they store the (finite) bias
+      float ln_rs = 0.f;   // rstd; rows beyond M keep 0 -> they store the (finite) bias
       if (C::kFold) {
         const int row = row_base + lane;
         if (row < M) {
@@ -315,7 +333,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               m2 += p[i].y + (float)LN_SLAB * d * d;
             }
           ln_rs = rsqrtf(m2 * inv_d + ep.ln_eps);
-          ln_nm = -mean * ln_rs;
+          if (EPI == EPI_LNFOLD_ACT_BF16 && ep.act == ACT_QUICK_GELU) ln_rs *= 0.5f;   // the bias is staged halved
         }
       }
       // LN fold, producer side: pull the first x tiles of this warp in while the main loop runs
@@ -347,6 +365,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int c = 0; c < NCH; ++c) {
             const int j = c % C::XBUFS;
             const uint32_t xt = stage_smem + j * EPI_X_TILE_BYTES + lane * 128;
+#if MMCM_STATS_EARLY
+            if (c >= 1) {   // refill the previous chunk's x buffer before touching this chunk
+              if (lane == 0) {
+                bulk_wait_read0();
+                const int cn = c - 1 + C::XBUFS;
+                if (cn < NCH) {
+                  const int jn = (c - 1) % C::XBUFS;
+                  const uint32_t bar = smem_u32(&bar_x[e][jn]);
+                  fence_proxy_async();
+                  mbar_expect_tx(bar, EPI_X_TILE_BYTES);
+                  tma_load_2d(&tmap_c, bar, stage_smem + jn * EPI_X_TILE_BYTES, col_base + cn * 32, row_base);
+                }
+              }
+              __syncwarp();
+            }
+#endif
             mbar_wait(smem_u32(&bar_x[e][j]), (xph >> j) & 1u);
             xph ^= 1u << j;
             uint32_t r[32];
@@ -380,7 +414,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               run_s += cs;
             }
             // the previous chunk's stores have read their tiles: its x buffer can take the chunk XBUFS ahead of it
-            if (c >= 1) {
+            if (!MMCM_STATS_EARLY && c >= 1) {
               if (lane == 0) {
                 bulk_wait_read0();
                 const int cn = c - 1 + C::XBUFS;
@@ -428,25 +462,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               tmem_ld32(t_row + (uint32_t)(c * 64), r);
               tmem_ld_wait();
               if (tr && c == 0) trace_stamp(ep, 11);
-              epi_pack_bf16<EPI>(ep, bias_smem + c * 256, r, &w[0], ln_rs, ln_nm, HALF_N * 4);
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256, r, &w[0], ln_rs);
             }
             {
               uint32_t r[32];
               tmem_ld32(t_row + (uint32_t)(c * 64 + 32), r);
               tmem_ld_wait();
-              epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16], ln_rs, ln_nm, HALF_N * 4);
+              epi_pack_bf16<EPI>(ep, bias_smem + c * 256 + 128, r, &w[16], ln_rs);
             }
             if (tr && c == 0) trace_stamp(ep, 14);
             if (tma_path) {
-              if (lane == 0) bulk_wait_read0();            // the previous chunk's store has finished reading the tile
+              const uint32_t sbuf = stage_smem + (cc % MMCM_EPI_NSTG) * EPI_TMA_STAGE_BYTES;
+              ++cc;
+              if (lane == 0) bulk_wait_read<MMCM_EPI_NSTG - 1>();   // the store that last used this tile has read it
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                sts128(stage_smem + lane * 128 + ((i ^ (lane & 7)) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                sts128(sbuf + lane * 128 + ((i ^ (lane & 7)) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
               fence_proxy_async();                          // generic-proxy writes -> visible to the TMA unit
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&tmap_c, stage_smem, col_base + c * 64, row_base);
+                tma_store_2d(&tmap_c, sbuf, col_base + c * 64, row_base);
                 bulk_commit();
               }
             } else {
@@ -461,12 +497,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t r[32];
             tmem_ld32(t_row + (uint32_t)(c * 32), r);
             tmem_ld_wait();
-            if (lane == 0) bulk_wait_read0();
+            const uint32_t sbuf = stage_smem + (cc % MMCM_EPI_NSTG) * EPI_TMA_STAGE_BYTES;
+            ++cc;
+            if (lane == 0) bulk_wait_read<MMCM_EPI_NSTG - 1>();
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 b = lds128(bias_smem + c * 128 + i * 16);
-              sts128(stage_smem + lane * 128 + ((i ^ (lane & 7)) << 4),
+              sts128(sbuf + lane * 128 + ((i ^ (lane & 7)) << 4),
                      __float_as_uint(__uint_as_float(r[4 * i]) + __uint_as_float(b.x)),
                      __float_as_uint(__uint_as_float(r[4 * i + 1]) + __uint_as_float(b.y)),
                      __float_as_uint(__uint_as_float(r[4 * i + 2]) + __uint_as_float(b.z)),
@@ -475,8 +513,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (ep.resid) tma_reduce_add_2d(&tmap_c, stage_smem, col_base + c * 32, row_base);   // x += acc + bias
-              else tma_store_2d(&tmap_c, stage_smem, col_base + c * 32, row_base);
+              if (ep.resid) tma_reduce_add_2d(&tmap_c, sbuf, col_base + c * 32, row_base);   // x += acc + bias
+              else tma_store_2d(&tmap_c, sbuf, col_base + c * 32, row_base);
               bulk_commit();
             }
           }

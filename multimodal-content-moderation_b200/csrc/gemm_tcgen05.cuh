@@ -29,7 +29,7 @@ namespace mmcm {
 // 0-3: every GEMM kernel.  4-6: CTA-pair kernel only -- LayerNorm folded into the GEMMs (gemm2_tcgen05.cuh, "LN fold"):
 //   EPI_RESID_STATS      x += acc + bias (fp32, in place), plus a bf16 copy of the updated rows and per-row
 //                        (sum, M2) partials over every 128-column slab  -> replaces the residual GEMM + half the LN pass
-//   EPI_LNFOLD_BF16      out = rstd * (acc - mean * colsum) + bias'   with acc = bf16(x) @ bf16(W * gamma)^T
+//   EPI_LNFOLD_BF16      out = rstd * acc + bias'   with acc = bf16(x) @ W'^T, W' = bf16(W * gamma, rows centred)
 //   EPI_LNFOLD_ACT_BF16  same, then the activation                    -> the other half: LN applied in the consumer
 enum Epi : int { EPI_BIAS_BF16 = 0, EPI_BIAS_ACT_BF16 = 1, EPI_BIAS_RESID_F32 = 2, EPI_PATCH_F32 = 3,
                  EPI_RESID_STATS = 4, EPI_LNFOLD_BF16 = 5, EPI_LNFOLD_ACT_BF16 = 6 };
@@ -45,10 +45,9 @@ struct EpiParams {
   int act;             // Act for EPI_BIAS_ACT_BF16
   const int* m_dev;    // optional device-side row count (<= M): packed variable-length text chunks
   // LN fold (EPI_RESID_STATS writes, EPI_LNFOLD_* read): float2 stats[slab][stats_pitch] = (sum, M2) of the row's
-  // 128-column slab; xb = bf16 copy of the updated residual rows; colsum[n] = sum_k bf16(W[n,k] * gamma[k])
+  // 128-column slab; xb = bf16 copy of the updated residual rows
   float2* stats;
   void* xb;
-  const float* colsum;
   int stats_pitch, ln_slabs;
   float ln_eps;
   long long* trace;    // dev tool (mmcm_debug_set_gemm_trace): per-CTA clock64 stamps, 16 slots per CTA; else nullptr
@@ -153,28 +152,32 @@ __device__ __forceinline__ void epi_chunk_bf16(const EpiParams& ep, const uint32
 
 // the same epilogue in two steps, for callers that want only 32 accumulator registers live at a time:
 // pack 32 fp32 accumulators (+ bias from smem, + activation) into 16 bf16x2 words ...
+// QuickGELU epilogues run on HALVED constants: the caller stages 0.5 * bias and passes 0.5 * rstd,
+// so the pre-activation arrives as h = x / 2 (exact: scaling by a power of two commutes with every rounding) and
+// x * sigmoid(1.702 x) = h + h * tanh(1.702 h) costs FMUL + MUFU + FFMA -- the LN-fold epilogue then issues exactly as
+// many instructions per element as the plain bias + QuickGELU one did (tools/gemm_bench_fold.py: fc1 +10 % before).
 template <int EPI>
 __device__ __forceinline__ void epi_pack_bf16(const EpiParams& ep, const uint32_t bias_smem, const uint32_t (&r)[32],
-                                              uint32_t* w, const float ln_rs = 0.f, const float ln_nm = 0.f,
-                                              const uint32_t colsum_off = 0) {
+                                              uint32_t* w, const float ln_rs = 0.f) {
   constexpr bool kFold = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16);
   constexpr bool kAct = (EPI == EPI_BIAS_ACT_BF16 || EPI == EPI_LNFOLD_ACT_BF16);
+  const bool halved = kAct && ep.act == ACT_QUICK_GELU;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * i + j]);
     const uint4 ba = lds128(bias_smem + i * 32), bb = lds128(bias_smem + i * 32 + 16);
-    if (kFold) {   // LN fold: rstd * acc - rstd * mean * colsum + bias'
-      const uint4 ca = lds128(bias_smem + colsum_off + i * 32), cb = lds128(bias_smem + colsum_off + i * 32 + 16);
-      v[0] = fmaf(v[0], ln_rs, fmaf(ln_nm, __uint_as_float(ca.x), __uint_as_float(ba.x)));
-      v[1] = fmaf(v[1], ln_rs, fmaf(ln_nm, __uint_as_float(ca.y), __uint_as_float(ba.y)));
-      v[2] = fmaf(v[2], ln_rs, fmaf(ln_nm, __uint_as_float(ca.z), __uint_as_float(ba.z)));
-      v[3] = fmaf(v[3], ln_rs, fmaf(ln_nm, __uint_as_float(ca.w), __uint_as_float(ba.w)));
-      v[4] = fmaf(v[4], ln_rs, fmaf(ln_nm, __uint_as_float(cb.x), __uint_as_float(bb.x)));
-      v[5] = fmaf(v[5], ln_rs, fmaf(ln_nm, __uint_as_float(cb.y), __uint_as_float(bb.y)));
-      v[6] = fmaf(v[6], ln_rs, fmaf(ln_nm, __uint_as_float(cb.z), __uint_as_float(bb.z)));
-      v[7] = fmaf(v[7], ln_rs, fmaf(ln_nm, __uint_as_float(cb.w), __uint_as_float(bb.w)));
+    if (kFold) {   // LN fold: rstd * acc + bias'  (the weight rows are centred, so acc already is (x - mean) . W*gamma)
+      v[0] = fmaf(v[0], ln_rs, __uint_as_float(ba.x)); v[1] = fmaf(v[1], ln_rs, __uint_as_float(ba.y));
+      v[2] = fmaf(v[2], ln_rs, __uint_as_float(ba.z)); v[3] = fmaf(v[3], ln_rs, __uint_as_float(ba.w));
+      v[4] = fmaf(v[4], ln_rs, __uint_as_float(bb.x)); v[5] = fmaf(v[5], ln_rs, __uint_as_float(bb.y));
+      v[6] = fmaf(v[6], ln_rs, __uint_as_float(bb.z)); v[7] = fmaf(v[7], ln_rs, __uint_as_float(bb.w));
+    } else if (halved) {   // h = 0.5 * (acc + bias) = fma(acc, 0.5, 0.5 * bias)
+      v[0] = fmaf(v[0], 0.5f, __uint_as_float(ba.x)); v[1] = fmaf(v[1], 0.5f, __uint_as_float(ba.y));
+      v[2] = fmaf(v[2], 0.5f, __uint_as_float(ba.z)); v[3] = fmaf(v[3], 0.5f, __uint_as_float(ba.w));
+      v[4] = fmaf(v[4], 0.5f, __uint_as_float(bb.x)); v[5] = fmaf(v[5], 0.5f, __uint_as_float(bb.y));
+      v[6] = fmaf(v[6], 0.5f, __uint_as_float(bb.z)); v[7] = fmaf(v[7], 0.5f, __uint_as_float(bb.w));
     } else {
       v[0] += __uint_as_float(ba.x); v[1] += __uint_as_float(ba.y); v[2] += __uint_as_float(ba.z); v[3] += __uint_as_float(ba.w);
       v[4] += __uint_as_float(bb.x); v[5] += __uint_as_float(bb.y); v[6] += __uint_as_float(bb.z); v[7] += __uint_as_float(bb.w);
@@ -182,7 +185,7 @@ __device__ __forceinline__ void epi_pack_bf16(const EpiParams& ep, const uint32_
     if (kAct) {
       if (ep.act == ACT_QUICK_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = quick_gelu_fast(v[j]);
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], tanh_approx(1.702f * v[j]), v[j]);   // v holds h = x / 2
       } else if (ep.act == ACT_GELU_TANH) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);

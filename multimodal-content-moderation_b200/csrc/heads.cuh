@@ -53,12 +53,45 @@ __device__ __forceinline__ float head_act(float v, int act) {
 constexpr int HEAD_NB = 4;
 static_assert(HEAD_SB * HEAD_NB == 32, "the butterfly below assumes 32 partial sums per lane");
 
+// ---- small batches: one sample group per CLUSTER --------------------------------------------------------------
+// With B <= 8 a single CTA streamed all 11.6 MB of fp32 head weights through one SM: 341 us, a quarter of the B = 1
+// latency.  Launched as a thread-block cluster (HEAD_CLUSTER CTAs per group of HEAD_SB samples), every CTA computes
+// 1 / HEAD_CLUSTER of the output columns of each Linear and stores them into the activation buffers of ALL CTAs of
+// the cluster through distributed shared memory; the cheap element-wise steps between the Linears are done
+// redundantly by everyone on its full local copy.  cluster size 1 (large batches) is the same code.
+constexpr int HEAD_CLUSTER = 8;
+__device__ __forceinline__ uint32_t head_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t head_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// CTA barrier + cluster barrier with release / acquire: DSMEM stores before it are visible to every CTA after it
+__device__ __forceinline__ void head_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void head_store_all(float* local, const float v, const uint32_t csize) {
+  if (csize == 1) { *local = v; return; }
+  const uint32_t la = smem_u32(local);
+  for (uint32_t r = 0; r < csize; ++r) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  }
+}
+
 __device__ __forceinline__ void block_linear(const float* __restrict__ W, const float* __restrict__ bias, const int N,
                                              const int K, const float* xs, const int ldx, float* ys,
                                              const int ldy, const int act) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int K4 = K >> 2;
-  for (int n0 = warp * HEAD_NB; n0 < N; n0 += nw * HEAD_NB) {
+  const uint32_t crank = head_cluster_rank(), csize = head_cluster_size();
+  for (int n0 = ((int)crank * nw + warp) * HEAD_NB; n0 < N; n0 += (int)csize * nw * HEAD_NB) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -99,7 +132,7 @@ __device__ __forceinline__ void block_linear(const float* __restrict__ W, const 
       }
     }
     const int s = lane / HEAD_NB, j = lane % HEAD_NB;
-    if (n0 + j < N) ys[s * ldy + n0 + j] = head_act(v[0] + (bias ? __ldg(bias + n0 + j) : 0.f), act);
+    if (n0 + j < N) head_store_all(ys + s * ldy + n0 + j, head_act(v[0] + (bias ? __ldg(bias + n0 + j) : 0.f), act), csize);
   }
 }
 
@@ -137,7 +170,7 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
   float* feat = z2 + HEAD_SB * fd;               // [SB][5 fd] = [fused | tp | vp | |tp-vp| | tp*vp]
   __shared__ float s_tp[HEAD_SB], s_ip[HEAD_SB];
 
-  const int s0 = blockIdx.x * HEAD_SB;
+  const int s0 = (blockIdx.x / head_cluster_size()) * HEAD_SB;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
 
@@ -153,25 +186,25 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
     s_tp[tid] = (s0 + tid < B) ? tpres[s0 + tid] : 0.f;
     s_ip[tid] = (s0 + tid < B) ? ipres[s0 + tid] : 0.f;
   }
-  __syncthreads();
+  head_sync();
 
   const float* tin = bufA;   // text feature rows, pitch ldt
   const float* vin = bufB;
   int ldt = HEAD_MAXD, ldv = HEAD_MAXD, dt = w.dt, dv = w.dv;
   if (w.text_head_w) {  // SigLIP: pooler_output = head(final_LN(x)[:, -1]); staged through `feat` (free until later)
     block_linear(w.text_head_w, w.text_head_b, w.dt, w.dt, bufA, HEAD_MAXD, feat, HEAD_MAXD, HA_NONE);
-    __syncthreads();
+    head_sync();
     for (int i = tid; i < HEAD_SB * w.dt; i += nthr) {
       const int s = i / w.dt, k = i - s * w.dt;
       bufA[s * HEAD_MAXD + k] = feat[s * HEAD_MAXD + k];
     }
-    __syncthreads();
+    head_sync();
   }
   if (w.head == 0) {
     if (w.text_proj) {  // CLIP: pooled -> projection_dim, no bias
       block_linear(w.text_proj, nullptr, w.dp, w.dt, bufA, HEAD_MAXD, z0, fd, HA_NONE);
       block_linear(w.vis_proj, nullptr, w.dp, w.dv, bufB, HEAD_MAXD, z1, fd, HA_NONE);
-      __syncthreads();
+      head_sync();
       tin = z0; vin = z1; ldt = ldv = fd; dt = dv = w.dp;
     }
     if (feat_t_out) {  // introspection: get_text_features / get_image_features outputs (before normalisation)
@@ -183,7 +216,7 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
         const int s = i / dv, k = i - s * dv;
         if (s0 + s < B) feat_v_out[(size_t)(s0 + s) * dv + k] = vin[s * ldv + k];
       }
-      __syncthreads();
+      head_sync();
     }
     // F.normalize(dim=-1, eps=1e-12) * presence   (fusion.py:188-189)
     for (int s = warp; s < 2 * HEAD_SB; s += nw) {
@@ -197,17 +230,17 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
       const float sc = (is_t ? s_tp[ss] : s_ip[ss]) / nrm;
       for (int k = lane; k < d; k += 32) r[k] *= sc;
     }
-    __syncthreads();
+    head_sync();
   }
   // proj_t / proj_i -> feat[:, fd:2fd], feat[:, 2fd:3fd]
   block_linear(w.proj_t_w, w.proj_t_b, fd, dt, tin, ldt, feat + fd, ldf, HA_NONE);
   block_linear(w.proj_i_w, w.proj_i_b, fd, dv, vin, ldv, feat + 2 * fd, ldf, HA_NONE);
-  __syncthreads();
+  head_sync();
   // zt, zi, gate(cat[tp, vp, presence])
   block_linear(w.g_t_w, w.g_t_b, fd, fd, feat + fd, ldf, z0, fd, HA_TANH);
   block_linear(w.g_i_w, w.g_i_b, fd, fd, feat + 2 * fd, ldf, z1, fd, HA_TANH);
   block_linear(w.gate_w, nullptr, fd, 2 * fd, feat + fd, ldf, z2, fd, HA_NONE);
-  __syncthreads();
+  head_sync();
   for (int i = tid; i < HEAD_SB * fd; i += nthr) {
     const int s = i / fd, n = i - s * fd;
     const float tpv = s_tp[s], ipv = s_ip[s];
@@ -222,24 +255,24 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
       feat[s * ldf + 4 * fd + n] = a * b;
     }
   }
-  __syncthreads();
+  head_sync();
 
   if (w.head == 0) {
     block_layernorm(feat, ldf, fd, w.ln_fused_g, w.ln_fused_b);      // ln_fused on the fused slice only
-    __syncthreads();
+    head_sync();
     block_layernorm(feat, ldf, 5 * fd, w.cls0_g, w.cls0_b);          // cls.0
-    __syncthreads();
+    head_sync();
     block_linear(w.cls1_w, w.cls1_b, fd, 5 * fd, feat, ldf, z0, fd, HA_GELU);   // cls.1 + GELU (Dropout: eval no-op)
-    __syncthreads();
+    head_sync();
     block_linear(w.cls4_w, w.cls4_b, w.n_out, fd, z0, fd, z1, fd, HA_NONE);     // cls.4
-    __syncthreads();
+    head_sync();
   } else {
     block_linear(w.shared_w, w.shared_b, fd, fd, feat, ldf, z0, fd, HA_GELU);   // shared_head
-    __syncthreads();
+    head_sync();
     if (w.hh > 0) {
       for (int j = 0; j < w.n_out; ++j) {
         block_linear(w.h0_w + (size_t)j * w.hh * fd, w.h0_b + (size_t)j * w.hh, w.hh, fd, z0, fd, z2, fd, HA_GELU);
-        __syncthreads();
+        head_sync();
         // Linear(hh, 1): one warp per sample
         for (int s = warp; s < HEAD_SB; s += nw) {
           float a = 0.f;
@@ -247,13 +280,14 @@ head_kernel(const HeadWeights w, const float* __restrict__ pooled_t, const float
           a = warp_sum(a);
           if (lane == 0) z1[s * fd + j] = a + __ldg(w.h3_b + j);
         }
-        __syncthreads();
+        head_sync();
       }
     } else {
       block_linear(w.h3_w, w.h3_b, w.n_out, fd, z0, fd, z1, fd, HA_NONE);
-      __syncthreads();
+      head_sync();
     }
   }
+  if (head_cluster_rank() != 0) return;   // every CTA of the cluster holds the same logits: one of them stores
   for (int i = tid; i < HEAD_SB * w.n_out; i += nthr) {
     const int s = i / w.n_out, n = i - s * w.n_out;
     if (s0 + s < B) {

@@ -267,8 +267,8 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
     CKR(get_tmap(&td, ep.xb, M, ep.ldo, -3, false));
   }
   if ((EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16) &&
-      (!ep.stats || !ep.colsum || !ep.bias || ep.ln_slabs < 1 || ep.ln_slabs > 8 || ep.ln_slabs * LN_SLAB != K))
-    return fail(MMCM_EINVAL, "gemm: EPI_LNFOLD needs stats, colsum, bias and K == 128 * slabs <= 1024");
+      (!ep.stats || !ep.bias || ep.ln_slabs < 1 || ep.ln_slabs > 8 || ep.ln_slabs * LN_SLAB != K))
+    return fail(MMCM_EINVAL, "gemm: EPI_LNFOLD needs stats, bias and K == 128 * slabs <= 1024");
   if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
   CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, td, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
   CK(cudaGetLastError());
@@ -488,11 +488,11 @@ __global__ void copy2d_kernel(const float* __restrict__ src, void* __restrict__ 
   }
 }
 
-// The layer norms are folded into the Linears that consume them (fold_ln_kernel): wqkv / w1 hold bf16(W * gamma),
-// bqkv / b1 the folded biases b + W beta, sqkv / s1 the column sums the LN-fold epilogue subtracts the mean with.
+// The layer norms are folded into the Linears that consume them (fold_ln_kernel): wqkv / w1 hold bf16(W * gamma) with
+// centred rows, bqkv / b1 the folded biases b + W beta.
 struct LayerW {
   bf16 *wqkv, *wo, *w1, *w2;
-  float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *sqkv, *s1;
+  float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
 };
 struct FoldJob {   // one fold_ln_kernel launch: staged fp32 W [N,K] and b [N] -> bf16 W*gamma, colsum, folded bias
   int64_t w_off, b_off;
@@ -500,7 +500,7 @@ struct FoldJob {   // one fold_ln_kernel launch: staged fp32 W [N,K] and b [N] -
   int N, K, q_rows;
   float q_scale;
   bf16* wout;
-  float *colsum, *bias_out;
+  float* bias_out;
 };
 struct TowerW {
   int D, H, L, F, act;
@@ -590,6 +590,7 @@ struct mmcm_handle_s {
   int opt_pooled_last = 1;   // last layer: out_proj / MLP / final LN only for the one row per sample that is pooled (exact)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
+  int opt_head_cluster = 1;   // B <= 144: the head kernel runs as clusters of 8 CTAs per 8 samples (heads.cuh)
   int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
   int last_chunk_text = 0, last_chunk_vis = 0;
   LaunchStats stats;
@@ -657,8 +658,6 @@ static int setup_tower(Eng* e, TowerW& t, const std::string& prefix, int D, int 
     CKR(dalloc(e, &w.b2, D));
     CKR(dalloc(e, &w.ln1g, D)); CKR(dalloc(e, &w.ln1b, D));
     CKR(dalloc(e, &w.ln2g, D)); CKR(dalloc(e, &w.ln2b, D));
-    CKR(dalloc(e, &w.sqkv, 3 * D));
-    CKR(dalloc(e, &w.s1, F));
     const std::string p = prefix + "encoder.layers." + std::to_string(i) + ".";
     const int64_t dd = (int64_t)D * D;
     // q/k/v_proj and fc1 consume a LayerNorm: staged in fp32, folded with its gamma / beta at finalize
@@ -683,8 +682,8 @@ static int setup_tower(Eng* e, TowerW& t, const std::string& prefix, int D, int 
     reg(e, p + "mlp.fc2.weight", (int64_t)D * F, w.w2, 1);
     reg(e, p + "mlp.fc2.bias", D, w.b2, 0);
     // dh^-1/2 = 0.125 goes into the q rows (exact: a power of two)
-    e->fold_jobs.push_back(FoldJob{o_wqkv, o_bqkv, w.ln1g, w.ln1b, 3 * D, D, D, qs, w.wqkv, w.sqkv, w.bqkv});
-    e->fold_jobs.push_back(FoldJob{o_w1, o_b1, w.ln2g, w.ln2b, F, D, 0, 1.0f, w.w1, w.s1, w.b1});
+    e->fold_jobs.push_back(FoldJob{o_wqkv, o_bqkv, w.ln1g, w.ln1b, 3 * D, D, D, qs, w.wqkv, w.bqkv});
+    e->fold_jobs.push_back(FoldJob{o_w1, o_b1, w.ln2g, w.ln2b, F, D, 0, 1.0f, w.w1, w.b1});
   }
   return MMCM_OK;
 }
@@ -792,6 +791,9 @@ static int setup_weights(Eng* e) {
       (clip && fusion && c.proj_dim > fd))
     return fail(MMCM_EINVAL, "head: unsupported widths (text %d vision %d fusion %d)", din_t, din_v, fd);
   if (C > fd) return fail(MMCM_EINVAL, "head: num_outputs %d > fusion_dim %d", C, fd);
+  // the SigLIP text head is staged through the 5*fd-wide interaction buffer with the tower's row pitch (heads.cuh)
+  if (!clip && 5 * fd < HEAD_MAXD)
+    return fail(MMCM_EINVAL, "head: siglip backend needs fusion_dim >= %d (got %d)", (HEAD_MAXD + 4) / 5, fd);
   CKR(f32("proj_t.weight", (int64_t)fd * din_t, &w.proj_t_w)); CKR(f32("proj_t.bias", fd, &w.proj_t_b));
   CKR(f32("proj_i.weight", (int64_t)fd * din_v, &w.proj_i_w)); CKR(f32("proj_i.bias", fd, &w.proj_i_b));
   CKR(f32("g_t.weight", (int64_t)fd * fd, &w.g_t_w)); CKR(f32("g_t.bias", fd, &w.g_t_b));
@@ -1009,11 +1011,11 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
   const int* slen = packed ? a.seq_len : nullptr;
   // h @ W^T with the LayerNorm in front of it: normalised rows x folded weights, or raw bf16 rows + LN-fold epilogue
   auto ln_linear = [&](const float* x, bf16* h, float2* stats, int pitch, const bf16* W, const float* bias,
-                       const float* colsum, int M, int N, bf16* out, int act, const int* mdev) -> int {
+                       int M, int N, bf16* out, int act, const int* mdev) -> int {
     EpiParams ep{};
     ep.bias = bias; ep.out = out; ep.ldo = N; ep.act = act; ep.m_dev = mdev;
     if (fold) {
-      ep.stats = stats; ep.stats_pitch = pitch; ep.colsum = colsum; ep.ln_slabs = D / LN_SLAB; ep.ln_eps = t.eps;
+      ep.stats = stats; ep.stats_pitch = pitch; ep.ln_slabs = D / LN_SLAB; ep.ln_eps = t.eps;
       return launch_gemm(h, W, M, N, D, act ? EPI_LNFOLD_ACT_BF16 : EPI_LNFOLD_BF16, ep, impl, st, S);
     }
     CKR(launch_layernorm(x, nullptr, nullptr, t.eps, M, D, nullptr, h, nullptr, st, S, mdev));   // affine part lives in W / bias
@@ -1034,7 +1036,7 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
     const LayerW& w = t.layers[i];
     const bool last = i == t.L - 1;
     // qkv = LN1(x) @ [Wq*s | Wk | Wv]^T + [bq*s | bk | bv]     HF clip :372, :313-319
-    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.wqkv, w.bqkv, w.sqkv, rows, 3 * D, a.qkv, ACT_NONE, rdev));
+    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.wqkv, w.bqkv, rows, 3 * D, a.qkv, ACT_NONE, rdev));
     // att = softmax(q k^T + mask) v                            HF clip :321-332
     CKR(launch_attention(a.qkv, kvalid, B, T, t.H, causal, a.att, st, S, sstart, slen));
     if (pooled_last && last) {
@@ -1043,14 +1045,14 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
       CK(cudaGetLastError());
       S->launches++;
       CKR(resid_linear(a.attp, w.wo, w.bo, a.xp, a.hp, a.statsp, a.mb, B, D, nullptr, true));
-      CKR(ln_linear(a.xp, a.hp, a.statsp, a.mb, w.w1, w.b1, w.s1, B, F, a.ffp, t.act, nullptr));
+      CKR(ln_linear(a.xp, a.hp, a.statsp, a.mb, w.w1, w.b1, B, F, a.ffp, t.act, nullptr));
       CKR(resid_linear(a.ffp, w.w2, w.b2, a.xp, nullptr, nullptr, 0, B, F, nullptr, false));   // the final LN reads x itself
       break;
     }
     // x = x + att @ Wo^T + bo                                  HF clip :334, :379
     CKR(resid_linear(a.att, w.wo, w.bo, a.x, a.h, a.stats, (int)a.rows, rows, D, rdev, true));
     // ff = act(LN2(x) @ W1^T + b1); x = x + ff @ W2^T + b2     HF clip :381-384, :347-351
-    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.w1, w.b1, w.s1, rows, F, a.ff, t.act, rdev));
+    CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.w1, w.b1, rows, F, a.ff, t.act, rdev));
     CKR(resid_linear(a.ff, w.w2, w.b2, a.x, a.h, a.stats, (int)a.rows, rows, F, rdev, !last));
   }
   return MMCM_OK;
@@ -1195,8 +1197,32 @@ static int run_head(Eng* e, const float* tp, const float* ip, int B, float* logi
   if (once.need()) CK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(MMCM_EINVAL, "head: fusion_dim %d needs too much shared memory", e->cfg.fusion_dim);
   const bool dbg = e->opt_debug_feats && e->cfg.head == MMCM_HEAD_FUSION;
-  CK(launch_k(head_kernel, dim3((B + HEAD_SB - 1) / HEAD_SB), dim3(HEAD_THREADS), smem, st, 
-      e->hw, e->pooled_t, e->pooled_v, tp, ip, B, logits, probs, dbg ? e->feat_t : nullptr, dbg ? e->feat_v : nullptr));
+  // few sample groups: a cluster of HEAD_CLUSTER CTAs per group splits every Linear's columns (heads.cuh)
+  const int groups = (B + HEAD_SB - 1) / HEAD_SB;
+  const int csize = (e->opt_head_cluster && groups * HEAD_CLUSTER <= g_num_sms) ? HEAD_CLUSTER : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * csize);
+  cfg.blockDim = dim3(HEAD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (t_opts->pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (csize > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = csize;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  CK(cudaLaunchKernelEx(&cfg, head_kernel, e->hw, (const float*)e->pooled_t, (const float*)e->pooled_v, tp, ip, B, logits,
+                        probs, dbg ? e->feat_t : (float*)nullptr, dbg ? e->feat_v : (float*)nullptr));
   CK(cudaGetLastError());
   e->stats.launches++;
   return MMCM_OK;
@@ -1450,7 +1476,7 @@ int mmcm_finalize_weights(mmcm_handle h) {
     for (const FoldJob& j : h->fold_jobs)
       CK(launch_k(fold_ln_kernel, dim3((j.N + 7) / 8), dim3(256), 0, nullptr, (const float*)(h->stage32 + j.w_off),
                   (const float*)(h->stage32 + j.b_off), j.gamma, j.beta, j.N, j.K, j.q_rows,
-                  j.q_scale, j.wout, j.colsum, j.bias_out));
+                  j.q_scale, j.wout, (float*)nullptr, j.bias_out));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     cudaFree(h->stage32);
@@ -1909,6 +1935,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     h->opts.attention_impl = (int)value;
   }
   else if (n == "ln_fold") h->opt_ln_fold = value != 0;
+  else if (n == "head_cluster") h->opt_head_cluster = value != 0;
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;
@@ -1951,11 +1978,11 @@ int mmcm_gemm_bf16(const void* A, const void* W, const float* bias, int32_t M, i
 
 // ---- LN fold, stand-alone (parity tests drive the same launchers the towers use) ----------------------------------
 int mmcm_fold_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
-                 int32_t q_rows, float q_scale, void* w_out, float* colsum_out, float* bias_out, void* stream) {
-  if (!W || !b || !gamma || !beta || !w_out || !colsum_out || !bias_out) return fail(MMCM_EINVAL, "null pointer");
-  if (N <= 0 || K <= 0) return fail(MMCM_EINVAL, "bad shape");
+                 int32_t q_rows, float q_scale, void* w_out, float* resid_out, float* bias_out, void* stream) {
+  if (!W || !b || !gamma || !beta || !w_out || !bias_out) return fail(MMCM_EINVAL, "null pointer");
+  if (N <= 0 || K <= 0 || K > 1024) return fail(MMCM_EINVAL, "fold_ln: need 0 < K <= 1024");
   CK(launch_k(fold_ln_kernel, dim3((N + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), W, b, gamma, beta, N, K,
-              q_rows, q_scale, reinterpret_cast<bf16*>(w_out), colsum_out, bias_out));
+              q_rows, q_scale, reinterpret_cast<bf16*>(w_out), resid_out, bias_out));
   CK(cudaGetLastError());
   return MMCM_OK;
 }
@@ -1978,13 +2005,12 @@ int mmcm_gemm_resid_stats(const void* A, const void* W, const float* bias, int32
                      reinterpret_cast<cudaStream_t>(stream), nullptr);
 }
 
-int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* colsum,
-                     const float* stats, int32_t M, int32_t N, int32_t K, float eps, int32_t act, void* out,
-                     void* stream) {
-  if (!xb || !w_folded || !bias_folded || !colsum || !stats || !out) return fail(MMCM_EINVAL, "null pointer");
+int mmcm_gemm_lnfold(const void* xb, const void* w_folded, const float* bias_folded, const float* stats, int32_t M,
+                     int32_t N, int32_t K, float eps, int32_t act, void* out, void* stream) {
+  if (!xb || !w_folded || !bias_folded || !stats || !out) return fail(MMCM_EINVAL, "null pointer");
   if (K % LN_SLAB != 0) return fail(MMCM_EINVAL, "gemm_lnfold: K must be a multiple of %d", LN_SLAB);
   EpiParams ep{};
-  ep.bias = bias_folded; ep.out = out; ep.ldo = N; ep.act = act; ep.colsum = colsum;
+  ep.bias = bias_folded; ep.out = out; ep.ldo = N; ep.act = act;
   ep.stats = reinterpret_cast<float2*>(const_cast<float*>(stats)); ep.stats_pitch = M; ep.ln_slabs = K / LN_SLAB;
   ep.ln_eps = eps;
   ep.trace = g_gemm_trace;

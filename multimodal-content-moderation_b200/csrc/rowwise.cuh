@@ -129,30 +129,49 @@ prep_rows_kernel(float* __restrict__ x, const float* __restrict__ gamma, const f
 
 // Weight side of the LN fold, run once per weight load (mmcm_finalize_weights): for output row n of a Linear that
 // consumes LayerNorm(x)
-//   Wout[n,k]   = bf16(scale_n * W[n,k] * gamma[k])        scale_n = dh^-1/2 for the q rows of the fused QKV matrix
-//   colsum[n]   = sum_k float(Wout[n,k])                    (of the ROUNDED operand: it must cancel what the MMA sums)
+//   g[n,k]      = scale_n * W[n,k] * gamma[k]              scale_n = dh^-1/2 for the q rows of the fused QKV matrix
+//   Wout[n,k]   = bf16(g[n,k] - mean_k g[n,:])             CENTRED rows: x . Wout[n] = (x - mean(x)) . g[n] for any x,
+//                                                          so the consumer never has to subtract mean(x) * colsum
 //   bias_out[n] = scale_n * (b[n] + sum_k W[n,k] * beta[k])
-// One warp per n.
+//   resid[n]    = sum_k float(Wout[n,k])                   what the bf16 rounding leaves of the zero row sum (optional;
+//                                                          the tests bound it: it multiplies mean(x) * rstd)
+// One warp per n; the row (K <= 1024) stays in registers between the two passes.
 __global__ void __launch_bounds__(256)
 fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
                const float* __restrict__ beta, const int N, const int K, const int q_rows, const float q_scale,
-               __nv_bfloat16* __restrict__ Wout, float* __restrict__ colsum, float* __restrict__ bias_out) {
+               __nv_bfloat16* __restrict__ Wout, float* __restrict__ resid, float* __restrict__ bias_out) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   const float sc = n < q_rows ? q_scale : 1.0f;
-  float cs = 0.f, bs = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = W[(size_t)n * K + k];
-    const __nv_bfloat16 wg = __float2bfloat16_rn(sc * w * gamma[k]);
-    Wout[(size_t)n * K + k] = wg;
-    cs += __bfloat162float(wg);
-    bs = fmaf(w, beta[k], bs);
+  float g[32];                      // K <= 1024
+  float gs = 0.f, bs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + 32 * i;
+    g[i] = 0.f;
+    if (k < K) {
+      const float w = W[(size_t)n * K + k];
+      g[i] = sc * w * gamma[k];
+      gs += g[i];
+      bs = fmaf(w, beta[k], bs);
+    }
   }
-  cs = warp_sum(cs);
+  const float mean = warp_sum(gs) / (float)K;
   bs = warp_sum(bs);
+  float rs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K) {
+      const __nv_bfloat16 wg = __float2bfloat16_rn(g[i] - mean);
+      Wout[(size_t)n * K + k] = wg;
+      rs += __bfloat162float(wg);
+    }
+  }
+  rs = warp_sum(rs);
   if (lane == 0) {
-    colsum[n] = cs;
+    if (resid) resid[n] = rs;
     bias_out[n] = sc * (b[n] + bs);
   }
 }

@@ -19,9 +19,16 @@ from . import prepost
 
 class BatchedScorer:
     def __init__(self, model: torch.nn.Module, class_names: Sequence[str], thresholds: Sequence[float],
-                 image_mean: Sequence[float] = (0.48145466, 0.4578275, 0.40821073),
-                 image_std: Sequence[float] = (0.26862954, 0.26130258, 0.27577711), max_batch: int = 1024):
+                 image_mean: Optional[Sequence[float]] = None, image_std: Optional[Sequence[float]] = None,
+                 max_batch: int = 1024):
+        """image_mean / image_std default to the image processor constants of the model's encoder family (CLIP's
+        dataset statistics, 0.5 / 0.5 for SigLIP) -- what `img_processor.image_mean` gives the reference's transform
+        (R/src/data/dataset.py:100-110)."""
+        from . import arch as A
         self.model = model.eval()
+        fam_mean, fam_std = A.IMAGE_NORM[model._arch.backend]
+        image_mean = fam_mean if image_mean is None else image_mean
+        image_std = fam_std if image_std is None else image_std
         self.class_names = list(class_names)
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":

@@ -13,31 +13,96 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(spec: str) -> set:
+    cpus = set()
+    for part in spec.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _numa_from_sysfs(device_index: int):
+    p = torch.cuda.get_device_properties(device_index)
+    bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+        node = int(f.read().strip())
+    if node < 0:
+        return None
+    with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+        return node, _parse_cpulist(f.read())
+
+
+def _numa_from_nvidia_smi(device_index: int):
+    """`nvidia-smi topo -m` prints, per GPU row, "CPU Affinity" and "NUMA Affinity" columns (the driver's own view;
+    it works inside containers whose sysfs hides the PCI numa_node)."""
+    import re
+    import subprocess
+    out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    header = None
+    for line in out.splitlines():
+        cols = [c for c in line.split("\t") if c.strip()]
+        if header is None and "CPU Affinity" in line:
+            header = [c.strip() for c in cols]
+            continue
+        if header and cols and cols[0].strip() == f"GPU{device_index}":
+            vals = [c.strip() for c in cols]
+            # the header has no entry above the row label: data column i sits under header[i - 1]
+            row = dict(zip(header, vals[1:]))
+            cpus = _parse_cpulist(row.get("CPU Affinity", ""))
+            node_s = row.get("NUMA Affinity", "").split(",")[0].split("-")[0]
+            node = int(node_s) if node_s.isdigit() else None
+            if cpus:
+                return node if node is not None else -1, cpus
+    return None
+
+
+def _prefer_numa_memory(node: int) -> bool:
+    """set_mempolicy(MPOL_PREFERRED, {node}): pages this thread faults in afterwards -- the pinned staging buffers --
+    come from the GPU's NUMA node even if the scheduler moves the thread.  Best effort (x86-64 / aarch64 syscall)."""
+    import ctypes
+    import platform
+    nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+    if nr is None or node < 0 or node >= 1024:
+        return False
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        return libc.syscall(nr, 1, ctypes.byref(mask), ctypes.c_ulong(1025)) == 0
+    except Exception:
+        return False
+
+
 def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards
     (first touch) and the H2D copies of `mmcm_forward_host` stay on the GPU's side of the machine.  One process per
-    GPU; a no-op (returns None) when the topology files are not readable."""
+    GPU.  Topology comes from sysfs, else from `nvidia-smi topo -m`; returns the node (-1: CPU affinity known, node
+    number not) or None when neither source answers."""
     import os
+    found = None
+    for probe in (_numa_from_sysfs, _numa_from_nvidia_smi):
+        try:
+            found = probe(device_index)
+        except Exception:
+            found = None
+        if found:
+            break
+    if not found:
+        return None
+    node, cpus = found
     try:
-        p = torch.cuda.get_device_properties(device_index)
-        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
         allowed = os.sched_getaffinity(0) & cpus
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return node
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
     except Exception:
         return None
-    return None
+    if node >= 0:
+        _prefer_numa_memory(node)
+    return node
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:

@@ -204,6 +204,43 @@ def test_cuda_graph_replay_matches_eager():
     assert m._engine.last_launch_count() > 100
 
 
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened", "clip_mtl_h0_hardened",
+                                  "siglip_fusion_hardened"])
+def test_head_cluster_is_bit_identical_to_single_cta(name):
+    """Small batches run the fused head as a cluster of 8 CTAs per 8 samples (columns split, DSMEM exchange): the
+    per-column arithmetic is unchanged, so logits and probabilities must not move by a bit."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    for B in (1, 8, 13, 100):
+        batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, B, seed=600 + B, edge_rows=B >= 8).items()}
+        m.set_option("head_cluster", 0)
+        y0 = m(**batch)["logits"].clone()
+        p0 = m.predict_proba(**batch).clone()
+        m.set_option("head_cluster", 1)
+        assert torch.equal(m(**batch)["logits"], y0)
+        assert torch.equal(m.predict_proba(**batch), p0)
+
+
+def test_cuda_graph_survives_buffer_growth():
+    """A graph captured at B=8 bakes the arena / pooled-buffer pointers.  A later, larger batch reallocates them; the
+    next B=8 call must not replay into freed memory: graphs are dropped with the buffers and re-captured."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    small = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 8, seed=23, edge_rows=True).items()}
+    big = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 256, seed=24).items()}
+    want_small = m(**small)["logits"].clone()
+    m.set_option("graph_max_batch", 64)
+    for _ in range(4):                                    # eager, eager, capture + replay, replay
+        assert torch.equal(m(**small)["logits"], want_small)
+    want_big = m(**big)["logits"].clone()                 # grows the arenas and the pooled buffers (B > 64)
+    for _ in range(4):
+        assert torch.equal(m(**small)["logits"], want_small)
+    assert torch.equal(m(**big)["logits"], want_big)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened"])
 def test_packed_varlen_text_is_bit_identical_to_dense(name):
     """varlen_text packs the causal CLIP text tower up to each sample's pooled row: same per-row arithmetic, so the

@@ -144,7 +144,7 @@ MMCM_API int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* v
  * packed text chunks). Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 /* Options (name -> meaning).  Every option is per handle; h == NULL edits the defaults that the stand-alone kernels
- * below use ("pdl", "tma_epilogue", "attention_impl" only):
+ * below use ("pdl", "tma_epilogue", "attention_impl", "narrow_tiles" only):
  *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)
  *   "micro_batch"      upper bound on the samples per internal pass of a tower (default 1024)
  *   "auto_chunk"       1 = pick, per tower, the chunk <= micro_batch whose GEMM tile counts fill whole rounds of the
@@ -165,6 +165,9 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  *   "head_cluster"     1 = default: for B <= 144 the fused head kernel runs as one thread-block cluster of 8 CTAs per
  *                      8 samples, each CTA computing an eighth of every Linear's columns and sharing them through
  *                      distributed shared memory (the B = 1 head: 341 -> ~45 us); bit-identical logits; 0 = one CTA
+ *   "narrow_tiles"     1 = default: GEMMs with a single 256-row block (B = 1 requests, the pooled-rows last layer)
+ *                      use 64-column (fp32 epilogues) / 128-column (bf16 epilogues) tiles so that 4x / 2x as many CTA
+ *                      pairs share the weight stream; 0 = 256-column tiles always.  Same per-element k order: identical bits.
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and

@@ -62,21 +62,24 @@ template <int TPAD, int QW>
 struct AttCfg {
   static constexpr int QROWS = QW * 16;
   static constexpr int BUF_BYTES = ((2 * TPAD + QROWS) * ATT_LD * 2 + TPAD + 15) / 16 * 16;
-  // long sequences (SigLIP vision, 196 tokens: 76 KB per item) keep ONE buffer so that two CTAs fit on an SM;
-  // short ones double-buffer (the next item streams in while the current one is computed)
+  // Occupancy beats software pipelining here.  The 77-token text kernel <80, 5> double-buffered its 34 KB item
+  // (69 KB, 3 CTAs = 15 warps per SM, 82 registers) and sat at 47 % of the HBM roofline with 41 % of the issue slots
+  // busy: latency bound, too few warps (profiles/r01_attention_layernorm_final_ncu_full.txt).  With ONE buffer and the
+  // register allocator held to 5 CTAs per SM (25 warps, 72 registers) the other CTAs' math covers a CTA's load phase:
+  // bench.py 56.5 k -> 58.0 k samples/s (profiles/r02_attention_occupancy.txt).  Items above the limit below are single
+  // buffered (SigLIP vision, 196 tokens: 76 KB per item, two CTAs per SM); smaller ones keep the double buffer.
 #ifndef MMCM_ATT_DB_LIMIT
-#define MMCM_ATT_DB_LIMIT (56 * 1024)
+#define MMCM_ATT_DB_LIMIT (30 * 1024)
 #endif
   static constexpr int NBUF = (BUF_BYTES > MMCM_ATT_DB_LIMIT) ? 1 : 2;
   static constexpr int SMEM_BYTES = NBUF * BUF_BYTES;
   static constexpr int QBLOCKS = (TPAD / 16 + QW - 1) / QW;
+  // min resident CTAs per SM the register allocator must allow (the text kernel: 5 x 160 threads x 80 registers)
+  static constexpr int MIN_CTAS = (TPAD == 80 && QW == 5) ? 5 : 1;
 };
 
-#ifndef MMCM_ATT_MINB
-#define MMCM_ATT_MINB 1   /* min resident CTAs per SM the register allocator must allow */
-#endif
 template <int TPAD, int QW>
-__global__ void __launch_bounds__(QW * 32, MMCM_ATT_MINB)
+__global__ void __launch_bounds__(QW * 32, AttCfg<TPAD, QW>::MIN_CTAS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const uint8_t* __restrict__ key_valid, const int* __restrict__ seq_start,
                  const int* __restrict__ seq_len, const int T_fixed, const int D, const int causal,

@@ -92,14 +92,13 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr int EPI_TMA_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled, 1 KB aligned
-// Staging tiles per epilogue warp for the TMA-store epilogues.  With ONE tile every chunk waited for the previous
-// chunk's bulk store to finish READING the tile before it could be refilled: a store-latency bubble per chunk that made
-// the K = 512 GEMMs epilogue bound (ncu, profiles/r02_gemm_shapes.txt: text qkv / fc1 at 52 / 49 % tensor pipe, 7.6 k
-// cycles per tile for a 4.1 k-cycle main loop).  With two, chunk c fills tile c & 1 while the store of chunk c - 1
-// drains the other (cp.async.bulk.wait_group.read 1).  The room comes from the operand ring: 4 stages instead of 5
-// (4 already saturate the TMA -> UMMA loop, tools/mainloop_probe.cu).
+// Staging tiles per epilogue warp for the TMA-store epilogues.  With one tile every chunk waits for the previous
+// chunk's bulk store to finish READING the tile before refilling it; two tiles (chunk c fills tile c & 1,
+// cp.async.bulk.wait_group.read 1) remove that wait but cost one operand-ring stage.  Measured (tools/gemm_bench_fold.py,
+// bench.py): two tiles + 4 stages 56.5 k samples/s, one tile + 5 stages 57.2 k -- the store wait is not what bounds the
+// K = 512 GEMMs, the deeper ring is worth more.  Kept as a build switch.
 #ifndef MMCM_EPI_NSTG
-#define MMCM_EPI_NSTG 2
+#define MMCM_EPI_NSTG 1
 #endif
 
 // ---- LN fold ------------------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ struct LaunchOpts {
   bool tma_epilogue = true;   // TMA tile-store / reduce-add epilogue of the pair GEMM
   int attention_impl = 0;     // 0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256
   int pair_limit = 0;         // > 0: cap the CTA pairs a GEMM launch may occupy (SM partitioning between the towers)
+  bool narrow_tiles = true;   // GEMMs with one row block (M <= 256) use 64 / 128-column tiles
 };
 static LaunchOpts g_default_opts;
 static thread_local const LaunchOpts* t_opts = &g_default_opts;
@@ -291,12 +292,22 @@ static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, co
     }
   }
   CKR(ensure_driver());
-  const int BN = (N % 256 == 0) ? 256 : 128;
+  int BN = (N % 256 == 0) ? 256 : 128;
+  // One row block (M <= 256: the online B = 1 path, the pooled-rows last layer): a 256-wide tile leaves N / 256 = 2-3
+  // CTA pairs streaming the whole weight matrix while 140 SMs idle -- fc2 took 20 us at B = 1, bound by what two SMs
+  // pull from L2 (tools/b1_launches.py).  Narrow tiles spread the weight stream: 64 columns for the fp32 epilogues
+  // (one 32-column chunk per epilogue warp), 128 for the bf16 ones.  The per-element k order is unchanged.
+  if (impl == 0 && M <= 256 && t_opts->narrow_tiles) {
+    if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32) { if (N % 64 == 0) BN = 64; }
+    else if constexpr (!kPairOnly) { if (N % 128 == 0) BN = 128; }
+  }
   CUtensorMap ta, tb;
   CKR(get_tmap(&ta, A, M, K, 128, false));
   if (impl == 0) {  // CTA-pair kernel: every CTA stages half of the B tile
     CKR(get_tmap(&tb, W, N, K, BN / 2, true));
     if (BN == 256) return launch_tc_pair<256, EPI>(ta, tb, ep, M, N, K, st);
+    if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32)
+      if (BN == 64) return launch_tc_pair<64, EPI>(ta, tb, ep, M, N, K, st);
     if constexpr (!kPairOnly) return launch_tc_pair<128, EPI>(ta, tb, ep, M, N, K, st);
   }
   if constexpr (!kPairOnly) {
@@ -590,6 +601,7 @@ struct mmcm_handle_s {
   int opt_pooled_last = 1;   // last layer: out_proj / MLP / final LN only for the one row per sample that is pooled (exact)
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
+  bool fold_forward = true;   // this forward runs the LN fold (opt_ln_fold and B >= kLnFoldMinBatch)
   int opt_head_cluster = 1;   // B <= 144: the head kernel runs as clusters of 8 CTAs per 8 samples (heads.cuh)
   int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
   int last_chunk_text = 0, last_chunk_vis = 0;
@@ -994,8 +1006,13 @@ static int ensure_batch(Eng* e, int64_t B) {
 // `pooled_last`: a.pool_row holds the one row per sample the caller reads after the last layer; the last layer then
 // runs out_proj / LN2 / MLP on those B rows only and leaves their residual in a.xp [B, D] (a.x keeps the last layer's
 // INPUT).  Row-wise ops on gathered rows give the same bits as on the full matrix.
+// Small batches (B < 16): the residual GEMM is a handful of tiles and the x tiles the EPI_RESID_STATS epilogue pulls in
+// are pure exposed latency (B = 1: 1.39 ms with the fold, 1.16 ms with the separate pass; B = 32: 1.30 vs 1.41 ms --
+// tools/latency.py), so they keep the separate normalisation kernel.  The choice is made once per forward from B, not
+// per micro-batch: every chunk of a forward runs the same arithmetic, so logits do not depend on the chunking.
+constexpr int kLnFoldMinBatch = 16;
 static bool use_ln_fold(const Eng* e, const TowerW& t) {
-  return e->opt_ln_fold && e->opt_gemm_impl == 0 && e->opts.tma_epilogue && t.D % 256 == 0 && t.D <= 1024;
+  return e->fold_forward && e->opt_gemm_impl == 0 && e->opts.tma_epilogue && t.D % 256 == 0 && t.D <= 1024;
 }
 
 // On entry with the LN fold on, a.h holds bf16(a.x) and a.stats the slab statistics of a.x (launch_prep_rows or the
@@ -1274,6 +1291,7 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
   e->stats.launches = 0;
   clear_gemm_events(e->stats);
   if (B == 0) return MMCM_OK;
+  e->fold_forward = e->opt_ln_fold && B >= kLnFoldMinBatch;
   const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min(B, e->opt_micro_batch);
   const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, e->opt_micro_batch, g_num_sms)
                                    : std::min(B, e->opt_micro_batch);
@@ -1753,6 +1771,7 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   CK(cudaSetDevice(e->device));
   if (B == 0) return MMCM_OK;
   OptsScope scope(&e->opts);
+  e->fold_forward = e->opt_ln_fold && B >= kLnFoldMinBatch;
   const mmcm_config& c = e->cfg;
   const size_t px_bytes = hpx.bytes_per_sample(c);
   const char* hsrc = hpx.u8 ? reinterpret_cast<const char*>(hpx.u8) : reinterpret_cast<const char*>(hpx.f32);
@@ -1913,6 +1932,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     if (d == "pdl") g_default_opts.pdl = value != 0;
     else if (d == "tma_epilogue") g_default_opts.tma_epilogue = value != 0;
     else if (d == "attention_impl" && value >= 0 && value <= 2) g_default_opts.attention_impl = (int)value;
+    else if (d == "narrow_tiles") g_default_opts.narrow_tiles = value != 0;
     else return fail(MMCM_EINVAL, "option '%s' = %lld cannot be set without a handle", name, (long long)value);
     return MMCM_OK;
   }
@@ -1936,6 +1956,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   }
   else if (n == "ln_fold") h->opt_ln_fold = value != 0;
   else if (n == "head_cluster") h->opt_head_cluster = value != 0;
+  else if (n == "narrow_tiles") h->opts.narrow_tiles = value != 0;
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;
   else if (n == "varlen_text") h->opt_varlen_text = value != 0;

@@ -59,12 +59,27 @@ class _B200ScoringModule(nn.Module):
         _register_flat(self, spec, syn.make_state_dict(spec, a, seed=seed, hardened=False))
         self._engine: Optional[Engine] = None
         self._engine_dirty = True
+        self._offloaded_to: Optional[int] = None   # CUDA device the engine lives on while the masters sit on the host
 
     # -- nn.Module hooks that can change parameter storage: mark the engine's repacked copy stale
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._engine_dirty = True
+        self._offloaded_to = None
         return out
+
+    def offload_master(self) -> "_B200ScoringModule":
+        """Move the fp32 master parameters back to host memory and keep scoring on the GPU.
+
+        The extension owns its own repacked copy (bf16 GEMM operands, fp32 norms / heads: 0.37 GB for CLIP-Fusion), so
+        after the push the 0.62 GB of fp32 `nn.Parameter`s on the device are dead weight for inference.  `state_dict()`
+        keeps working (host tensors); `.to(device)` / `load_state_dict` bring the usual behaviour back."""
+        dev = self._device_index()
+        self._ensure_engine(dev)
+        super()._apply(lambda t: t.cpu())
+        self._offloaded_to = dev
+        self._engine_dirty = False
+        return self
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         out = super().load_state_dict(state_dict, strict=strict, assign=assign)
@@ -84,6 +99,8 @@ class _B200ScoringModule(nn.Module):
         self._ensure_engine(self._device_index()).save_packed(path)
 
     def _device_index(self) -> int:
+        if self._offloaded_to is not None:
+            return self._offloaded_to
         p = next(self.parameters())
         if not p.is_cuda:
             raise RuntimeError("the B200 scoring path has no CPU fallback: move the model to a CUDA device first")

@@ -30,7 +30,8 @@ class BatchedScorer:
         image_mean = fam_mean if image_mean is None else image_mean
         image_std = fam_std if image_std is None else image_std
         self.class_names = list(class_names)
-        self.device = next(model.parameters()).device
+        self.device = torch.device("cuda", model._device_index()) if hasattr(model, "_device_index") \
+            else next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("BatchedScorer needs the model on a CUDA device: no CPU fallback")
         self.thresholds = torch.tensor(list(thresholds), dtype=torch.float32, device=self.device)

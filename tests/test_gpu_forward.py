@@ -26,13 +26,24 @@ def _rel_l2(x, ref):
     return (x - ref).norm().item() / max(ref.norm().item(), 1e-12)
 
 
-# Hardened-init gate, as a fraction of the batch logit std (SURVEY 8d proposed 5 %; what this build measures is
-# 1.2-1.5 % for the Fusion / SigLIP heads and ~3 % for the MTL heads, whose per-task logits are a 512-term fp32 dot
-# product of bf16-encoder features with x4-scaled weights).  A regression that doubles the error fails.
-REL_GATE = {"fusion": 0.025, "mtl": 0.045}
+# Hardened-init gate, as a fraction of the batch logit std (SURVEY 8d proposed 5 % max-abs for every model).  Measured
+# on B200 over 5 input seeds x 24 samples (tools/gate_survey.py, profiles/r02_gate_survey.txt), max-abs error in % of
+# the std, LN-fold path / separate-LayerNorm path:
+#     CLIP-Fusion 1.0-1.8 / 0.9-1.3      SigLIP-Fusion 1.8-3.0 / 2.2-3.2      CLIP-MTL 2.8-4.3 / 2.6-5.4
+# (MTL: each task logit is a 512-term fp32 dot product of bf16-encoder features with x4-scaled weights and no
+# LayerNorm in the head; SigLIP: 196-token towers, GELU-tanh).  The error is noise-like, so its maximum over a batch
+# moves with the batch; the gate is therefore two-sided: a max-abs bound ~1.4x the largest value seen, and an RMS bound
+# at 40 % of it, which a systematic defect (wrong bias, wrong mask, one bad tile) breaks long before the maximum moves.
+REL_GATE = {"clip_fusion": 0.025, "siglip_fusion": 0.045, "mtl": 0.07}
 
 
-def _gate(logits, ref, hardened, kind="fusion"):
+def _gate_key(kind, arch=None):
+    if kind == "mtl":
+        return "mtl"
+    return "siglip_fusion" if (arch is not None and arch.backend == 1) else "clip_fusion"
+
+
+def _gate(logits, ref, hardened, kind="fusion", arch=None):
     """Official gate on default init (BASELINE.json north_star); relative gate on hardened init."""
     err = (logits - ref).abs().max().item()
     p, pr = torch.sigmoid(logits), torch.sigmoid(ref)
@@ -42,8 +53,10 @@ def _gate(logits, ref, hardened, kind="fusion"):
         far = (pr - 0.5).abs() > 1e-3
     else:
         spread = ref.std().item()
-        rel = REL_GATE[kind]
+        rel = REL_GATE[_gate_key(kind, arch)]
+        rms = (logits - ref).pow(2).mean().sqrt().item()
         assert err <= rel * spread, f"logit max-abs {err} vs {100 * rel:.1f}% of std {spread}"
+        assert rms <= 0.4 * rel * spread, f"logit rms error {rms} vs {40 * rel:.1f}% of std {spread}"
         # sigmoid is 1/4-Lipschitz: the probability gate follows from the logit gate
         assert (p - pr).abs().max().item() <= 0.25 * rel * spread
         far = (pr - 0.5).abs() > 0.25 * rel * spread
@@ -62,7 +75,7 @@ def test_forward_matches_reference_golden(name):
     logits = out["logits"].float().cpu()
     ref = torch.from_numpy(gold["logits"])
     hardened = GOLDEN_CASES[name][4]
-    _gate(logits, ref, hardened, kind)
+    _gate(logits, ref, hardened, kind, a)
     if kind == "fusion":
         assert abs(out["loss"].item() - float(gold["loss"])) <= 0.05 * max(1.0, float(gold["loss"]))
     # stage-wise: pooled tower outputs / projected features, relative L2 (bf16 GEMM chain measures 4-8e-3)
@@ -91,7 +104,7 @@ def test_forward_matches_oracle_ragged_batches(name, B, mb, streams):
     m.set_option("micro_batch", mb)
     m.set_option("streams", streams)
     logits = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
-    _gate(logits, ref, True, kind)
+    _gate(logits, ref, True, kind, a)
     # determinism / idempotence: the same call again gives bit-identical logits
     again = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
     assert torch.equal(logits, again)
@@ -222,6 +235,58 @@ def test_head_cluster_is_bit_identical_to_single_cta(name):
         assert torch.equal(m.predict_proba(**batch), p0)
 
 
+def test_offload_master_keeps_scoring_and_frees_device_memory():
+    """`offload_master()`: the fp32 nn.Parameters go back to the host, the extension's repacked copy keeps scoring."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    batch = {k: v.to("cuda:0") for k, v in syn.make_inputs(a, 8, seed=44, edge_rows=True).items()}
+    want = m(**batch)["logits"].clone()
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    m.offload_master()
+    torch.cuda.synchronize()
+    assert not next(m.parameters()).is_cuda
+    assert before - torch.cuda.memory_allocated() > 500e6          # ~0.62 GB of fp32 masters left the device
+    assert torch.equal(m(**batch)["logits"], want)
+    assert set(m.state_dict()) == set(sd)
+    m.to("cuda:0")                                                # the usual behaviour comes back
+    assert next(m.parameters()).is_cuda and torch.equal(m(**batch)["logits"], want)
+
+
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened", "siglip_fusion_hardened"])
+def test_ln_fold_and_separate_pass_agree(name):
+    """ln_fold (default for B >= 16): LayerNorm inside the residual / qkv / fc1 GEMMs; ln_fold=0: a separate
+    normalisation kernel in front of the same folded weights.  Both must pass the oracle gate and agree with each other
+    to bf16-noise level; batches below 16 always take the separate pass."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    batch = syn.make_inputs(a, 24, seed=808, edge_rows=True)
+    with torch.no_grad():
+        ref = oracle_forward(kind, a, sd, batch)
+    d = {k: v.to("cuda:0") for k, v in batch.items()}
+    m.set_option("ln_fold", 1)
+    y1 = m(**d)["logits"].cpu()
+    n1 = m._engine.last_launch_count()
+    m.set_option("ln_fold", 0)
+    y0 = m(**d)["logits"].cpu()
+    n0 = m._engine.last_launch_count()
+    e1, e0 = (y1 - ref).abs().max().item(), (y0 - ref).abs().max().item()
+    print(f"{name}: fold {100 * e1 / ref.std().item():.2f} % / separate pass {100 * e0 / ref.std().item():.2f} % of std")
+    _gate(y1, ref, True, kind, a)
+    _gate(y0, ref, True, kind, a)
+    assert e1 <= 2.0 * e0 + 1e-3                          # the fold must not be systematically noisier (survey: 0.7-1.3x)
+    # two noise-like errors of the size the gate allows: their difference obeys the same bound
+    assert (y1 - y0).abs().max().item() <= REL_GATE[_gate_key(kind, a)] * ref.std().item()
+    assert n1 < n0 - 40                                   # two LayerNorm launches per layer and tower are gone
+    m.set_option("ln_fold", 1)
+    small = {k: v[:8].contiguous() for k, v in d.items()}
+    ys = m(**small)["logits"].cpu()
+    m.set_option("ln_fold", 0)
+    assert torch.equal(m(**small)["logits"].cpu(), ys)    # B < 16: the option does not change the path
+
+
 def test_cuda_graph_survives_buffer_growth():
     """A graph captured at B=8 bakes the arena / pooled-buffer pointers.  A later, larger batch reallocates them; the
     next B=8 call must not replay into freed memory: graphs are dropped with the buffers and re-captured."""
@@ -291,7 +356,7 @@ def test_tiny_batches_and_short_sequences(B, S):
         got = m(**{k: v.to("cuda:0") for k, v in batch.items()})["logits"].cpu()
         assert got.shape == (B, 5)
         err = (got - ref).abs().max().item()
-        assert err <= REL_GATE["fusion"] * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # of the hardened logit spread
+        assert err <= REL_GATE["clip_fusion"] * 3.35, f"B={B} S={S} varlen={varlen}: {err}"   # of the hardened logit spread
 
 
 def test_two_models_in_one_process_do_not_interfere():
@@ -433,7 +498,7 @@ def test_oracle_parity_at_baseline_batch_sizes(model, B, hardened):
     sub = {k: v[idx].contiguous() for k, v in batch.items()}
     with torch.no_grad():
         ref = oracle_forward(kind, a, sd, sub)
-    _gate(full[idx], ref, hardened, kind)
+    _gate(full[idx], ref, hardened, kind, a)
     # the same rows as their own small batch: identical bits (row-wise arithmetic, no cross-sample op anywhere)
     small = m(**{k: v.to("cuda:0") for k, v in sub.items()})["logits"].cpu()
     assert torch.equal(small, full[idx])

@@ -211,6 +211,44 @@ def test_gemm_lnfold_matches_layernorm_linear(lib, M, N, K, act):
         assert err.max().item() <= max(4 * base, 4e-2), f"fold {err.max().item()} vs separate pass {base}"
 
 
+@pytest.mark.parametrize("M", [1, 50, 77, 256])
+@pytest.mark.parametrize("epi,N,K", [(0, 2304, 768), (1, 2048, 512), (2, 768, 3072), (2, 512, 512), (3, 768, 3072)])
+def test_gemm_narrow_tiles_bit_identical(lib, M, epi, N, K):
+    """GEMMs with one 256-row block run 64 / 128-column tiles (more CTA pairs share the weight stream).  The k order of
+    every output element is the same as with 256-column tiles, so the results must be identical bits -- which is what
+    keeps the pooled-rows last layer (M = B) bit-identical to the all-rows path."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + epi)
+    if epi == 3:
+        M = max(49, (M // 49) * 49)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    pos = torch.randn(50, N, device="cuda", generator=g)
+    x0 = torch.randn(M + M // 49 + 1, N, device="cuda", generator=g)
+    outs = []
+    for narrow in (1, 0):
+        _check(lib.mmcm_set_option(None, b"narrow_tiles", narrow))
+        if epi in (0, 1):
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, epi, 1, out.data_ptr(), None,
+                                      None, 0, 0, 0, _stream()))
+        elif epi == 2:
+            out = x0[:M].clone()
+            _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 2, 0, out.data_ptr(),
+                                      out.data_ptr(), None, 0, 0, 0, _stream()))
+        else:
+            out = x0.clone()
+            _check(lib.mmcm_gemm_bf16(A.data_ptr(), W.data_ptr(), None, M, N, K, 3, 0, out.data_ptr(), None,
+                                      pos.data_ptr(), 49, 50, 0, _stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    _check(lib.mmcm_set_option(None, b"narrow_tiles", 1))
+    assert torch.equal(outs[0], outs[1])
+    if epi == 2:
+        ref = x0[:M] + A.float() @ W.float().t() + bias
+        assert (outs[0] - ref).abs().max().item() < 2e-3
+
+
 def test_gemm_rejects_bad_shapes(lib):
     A = torch.zeros(4, 96, device="cuda", dtype=torch.bfloat16)
     W = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)

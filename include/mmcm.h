@@ -143,6 +143,11 @@ MMCM_API int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* v
  * mmcm_set_option(h, "time_gemms", 1); also returns the FLOPs they EXECUTED (2*M*N*K with the live row count of
  * packed text chunks). Synchronises the device. */
 MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
+/* The same, restricted to the launches with one epilogue (MMCM_EPI_*), plus their ALGORITHMIC DRAM bytes (A and W in
+ * bf16 once, the epilogue's reads / writes per output element): the residual GEMMs (EPI_RESID_STATS) are bound by the
+ * fp32 residual stream in HBM, the others by the tensor pipe -- bench.py reports them apart. */
+MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out, double* flops_out, double* bytes_out,
+                                int64_t* launches_out);
 /* Options (name -> meaning).  Every option is per handle; h == NULL edits the defaults that the stand-alone kernels
  * below use ("pdl", "tma_epilogue", "attention_impl", "narrow_tiles" only):
  *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)
@@ -190,6 +195,9 @@ MMCM_API const char* mmcm_version(void);
 #define MMCM_EPI_BIAS_ACT_BF16 1   /* out bf16 = act(acc + bias)                             */
 #define MMCM_EPI_BIAS_RESID_F32 2  /* out fp32 = acc + bias + resid (resid may alias out)    */
 #define MMCM_EPI_PATCH_F32 3       /* out fp32[(r/P)*T+off+r%P] = acc + bias? + pos[off+r%P] */
+#define MMCM_EPI_RESID_STATS 4     /* mmcm_gemm_resid_stats: x += acc + bias, bf16 copy, row statistics */
+#define MMCM_EPI_LNFOLD_BF16 5     /* mmcm_gemm_lnfold, act = 0                                  */
+#define MMCM_EPI_LNFOLD_ACT_BF16 6 /* mmcm_gemm_lnfold, act != 0                                 */
 
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): A, W bf16 row-major device pointers (K % 64 == 0, N % 128 == 0).
  * impl 0 = tcgen05/TMEM/TMA kernel on CTA pairs (cta_group::2, 256 x BLOCK_N tiles), 1 = SIMT validation kernel,

@@ -221,7 +221,7 @@ static int get_sched(cudaStream_t st, int** out) {
 struct LaunchStats {
   int64_t launches = 0;
   bool time_gemms = false;
-  struct GemmRec { cudaEvent_t e0, e1; double flops_per_row; int m_host; const int* m_dev; };
+  struct GemmRec { cudaEvent_t e0, e1; double flops_per_row; int m_host; const int* m_dev; int epi, N, K; };
   std::vector<GemmRec> gemm_events;      // per-GEMM CUDA events (time_gemms) + what is needed to count EXECUTED FLOPs
   int text_chunk = 0;                    // packed text chunks of this forward (each owns one device row counter)
 };
@@ -345,7 +345,7 @@ static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int ep
     stats->launches++;
     if (stats->time_gemms) {
       CK(cudaEventRecord(e1, st));
-      stats->gemm_events.push_back(LaunchStats::GemmRec{e0, e1, 2.0 * (double)N * K, M, ep.m_dev});
+      stats->gemm_events.push_back(LaunchStats::GemmRec{e0, e1, 2.0 * (double)N * K, M, ep.m_dev, epi, N, K});
     }
   }
   return MMCM_OK;
@@ -1902,12 +1902,21 @@ int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* vision_chu
   return MMCM_OK;
 }
 
-int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
+// algorithmic DRAM bytes of one GEMM launch: A (bf16), W (bf16) and what the epilogue reads / writes per output element
+static double gemm_algorithmic_bytes(int epi, double m, int N, int K) {
+  static const double out_bytes[] = {2, 2, 8 /* fp32 read + write */, 4, 10 /* fp32 read + write, bf16 copy */, 2, 2};
+  return m * K * 2.0 + (double)N * K * 2.0 + m * N * out_bytes[epi];
+}
+
+static int gemm_time_impl(mmcm_handle h, int epi, double* ms_out, double* flops_out, int64_t* launches_out,
+                          double* bytes_out = nullptr) {
   if (!h) return fail(MMCM_EINVAL, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  double ms = 0, flops = 0;
+  double ms = 0, flops = 0, bytes = 0;
+  int64_t n = 0;
   for (auto& p : h->stats.gemm_events) {
+    if (epi >= 0 && p.epi != epi) continue;
     float t = 0;
     CK(cudaEventElapsedTime(&t, p.e0, p.e1));
     ms += t;
@@ -1917,11 +1926,24 @@ int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* la
       if (m > p.m_host) m = p.m_host;
     }
     flops += p.flops_per_row * m;
+    bytes += gemm_algorithmic_bytes(p.epi, m, p.N, p.K);
+    ++n;
   }
+  if (bytes_out) *bytes_out = bytes;
   if (ms_out) *ms_out = ms;
   if (flops_out) *flops_out = flops;
-  if (launches_out) *launches_out = (int64_t)h->stats.gemm_events.size();
+  if (launches_out) *launches_out = n;
   return MMCM_OK;
+}
+
+int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
+  return gemm_time_impl(h, -1, ms_out, flops_out, launches_out);
+}
+
+int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out, double* flops_out, double* bytes_out,
+                       int64_t* launches_out) {
+  if (epilogue < 0 || epilogue > EPI_LNFOLD_ACT_BF16) return fail(MMCM_EINVAL, "unknown epilogue %d", epilogue);
+  return gemm_time_impl(h, epilogue, ms_out, flops_out, launches_out, bytes_out);
 }
 
 int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {

@@ -240,7 +240,12 @@ class Engine:
         L.check(self.lib.mmcm_last_chunks(self._h, C.byref(t), C.byref(v)))
         return t.value, v.value
 
-    def gemm_time(self):
-        ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
-        L.check(self.lib.mmcm_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
-        return ms.value, fl.value, n.value
+    def gemm_time(self, epilogue: Optional[int] = None):
+        """(ms, executed FLOPs, launches) of the GEMM launches of the last forward run with option time_gemms = 1;
+        `epilogue` restricts the sum to one MMCM_EPI_* kind."""
+        ms, fl, by, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+        if epilogue is None:
+            L.check(self.lib.mmcm_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+            return ms.value, fl.value, n.value
+        L.check(self.lib.mmcm_gemm_time_epi(self._h, int(epilogue), C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)))
+        return ms.value, fl.value, by.value, n.value

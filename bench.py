@@ -467,8 +467,15 @@ def main():
 
         # what the box can deliver to all GPUs at once: the ceiling of the fp32-pixel e2e leg above
         mine, agg = h2d_probe(dev, world)
+        bound = agg * 1e9 / (in_bytes / B)
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / bound
+        e2e["frac_of_device_resident"] = e2e["value"] / value
+        if e2e["value"] > 0.75 * bound:
+            e2e["bound_by"] = ("host->device bandwidth of this box: all ranks together move "
+                               f"{agg:.0f} GB/s of pinned memory ({mine:.1f} GB/s on this rank), the fp32 pixel_values "
+                               f"contract needs {value / world * (in_bytes / B) / 1e9:.1f} GB/s per GPU at the device-resident rate")
         e2e["h2d_ceiling"] = {"pinned_h2d_gbs_this_rank": mine, "pinned_h2d_gbs_all_ranks": agg,
-                              "samples_per_s_bound": agg * 1e9 / (in_bytes / B),
+                              "samples_per_s_bound": bound,
                               "note": "all ranks copy 256 MiB pinned buffers concurrently (CUDA events); bound = aggregate "
                                       "bandwidth / input bytes per sample of the reference's fp32 pixel_values contract"}
 

@@ -173,6 +173,9 @@ MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out,
  *   "narrow_tiles"     1 = default: GEMMs with a single 256-row block (B = 1 requests, the pooled-rows last layer)
  *                      use 64-column (fp32 epilogues) / 128-column (bf16 epilogues) tiles so that 4x / 2x as many CTA
  *                      pairs share the weight stream; 0 = 256-column tiles always.  Same per-element k order: identical bits.
+ *   "split_k"          1 = default: in forwards with B < 16 the residual GEMMs (out_proj, fc2) split their K loop over
+ *                      up to 4 CTA pairs per tile; the partial sums are added to the residual stream, in a fixed order,
+ *                      by the LayerNorm kernel that follows (deterministic; no reduction launch); 0 = one pair per tile
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and

@@ -48,17 +48,32 @@ def is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile if missing or older than its sources; returns the path of the shared library."""
+    """Compile if missing or older than its sources; returns the path of the shared library.
+
+    Several processes may get here at once (one rank per GPU under torchrun, pytest-xdist workers): an exclusive file
+    lock serialises them, the staleness check is repeated under the lock, and every process compiles into its own
+    temporary file before the atomic rename."""
+    import fcntl
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH + ".tmp", os.path.join(CSRC, "mmcm.cu")]
-    if verbose:
-        print("[build]", " ".join(cmd), flush=True)
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libmmcm.so")
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():       # another process built it while this one waited
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "mmcm.cu")]
+            if verbose:
+                print("[build]", " ".join(cmd), flush=True)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libmmcm.so")
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -213,24 +213,29 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   // packed variable-length text: the live row count is produced on the device by the previous kernel
   const int M = ep.m_dev ? min(__ldg(ep.m_dev), M_host) : M_host;
   const int tiles_m = (M + C::BLOCK_M - 1) / C::BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
+  // split-K: only the fp32 store epilogue can hold partial sums (EpiParams::ksplit)
+  const int ksplit = (EPI == EPI_BIAS_RESID_F32 && ep.ksplit > 1) ? ep.ksplit : 1;
+  const int kb_per = num_kb / ksplit;
+  const int num_tiles = tiles_m * tiles_n * ksplit;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int mn = tile / ksplit, ks = tile - mn * ksplit;
+      const int m_blk = mn / tiles_n, n_blk = mn - m_blk * tiles_n;
       const int a_row = m_blk * C::BLOCK_M + (int)rank * 128;
       const int b_row = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < kb_per; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
         if (lane == 0) {
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const int kcol = (ks * kb_per + kb) * C::BLOCK_K;
           if (leader) mbar_expect_tx(full, 2 * C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
-          tma_load_2d_pair(&tmap_a, full, sa, kb * C::BLOCK_K, a_row);
-          tma_load_2d_pair(&tmap_b, full, sa + C::A_BYTES, kb * C::BLOCK_K, b_row);
+          tma_load_2d_pair(&tmap_a, full, sa, kcol, a_row);
+          tma_load_2d_pair(&tmap_b, full, sa + C::A_BYTES, kcol, b_row);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -245,7 +250,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);   // both CTAs' epilogues have drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < kb_per; ++kb) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (lane == 0) {
@@ -257,7 +262,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k)
             umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           umma_commit_pair(smem_u32(&bar_empty[stage]));
-          if (kb == num_kb - 1) {
+          if (kb == kb_per - 1) {
             umma_commit_pair(smem_u32(&bar_tfull[as]));
             if (tile == pair) trace_stamp(ep, 3);
             trace_stamp(ep, 6);
@@ -284,9 +289,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint32_t xph = 0;   // kStats: phase bit per x buffer
     uint32_t cc = 0;    // TMA-store epilogues: running chunk counter -> staging tile cc % MMCM_EPI_NSTG
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int mn = tile / ksplit, ks = tile - mn * ksplit;
+      const int m_blk = mn / tiles_n, n_blk = mn - m_blk * tiles_n;
       const int row_base = m_blk * C::BLOCK_M + (int)rank * 128 + lg * 32;
       const int col_base = n_blk * BLOCK_N + ch * HALF_N;
+      const int out_row = row_base + ks * ep.part_rows;          // split-K: plane ks of the partial-sum buffer
       float4 xa[8];
       float4 fb[HALF_N / 32];
       if (kF32 && !tma_path) {
@@ -301,8 +308,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const float hs = (kActEpi && ep.act == ACT_QUICK_GELU) ? 0.5f : 1.0f;
 #pragma unroll
         for (int j = lane; j < HALF_N / 4; j += 32) {
-          const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b = (ep.bias && ks == 0) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col_base) + j)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           sts128(bias_smem + j * 16, __float_as_uint(b.x * hs), __float_as_uint(b.y * hs), __float_as_uint(b.z * hs),
                  __float_as_uint(b.w * hs));
         }
@@ -513,7 +520,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             __syncwarp();
             if (lane == 0) {
               if (ep.resid) tma_reduce_add_2d(&tmap_c, sbuf, col_base + c * 32, row_base);   // x += acc + bias
-              else tma_store_2d(&tmap_c, sbuf, col_base + c * 32, row_base);
+              else tma_store_2d(&tmap_c, sbuf, col_base + c * 32, out_row);
               bulk_commit();
             }
           }

@@ -50,6 +50,10 @@ struct EpiParams {
   void* xb;
   int stats_pitch, ln_slabs;
   float ln_eps;
+  // split-K (CTA-pair kernel, fp32 store epilogue only): tile t covers k-blocks [ks, ks + 1) * K / (64 ksplit) of output
+  // tile t / ksplit and stores its partial sums into plane ks of `out` (planes part_rows rows apart); the bias goes into
+  // plane 0.  Whoever reads the result adds the planes in order (layernorm_kernel) -- deterministic, no inter-CTA waits.
+  int ksplit, part_rows;
   long long* trace;    // dev tool (mmcm_debug_set_gemm_trace): per-CTA clock64 stamps, 16 slots per CTA; else nullptr
 };
 

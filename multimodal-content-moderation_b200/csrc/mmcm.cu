@@ -250,7 +250,7 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
   auto kern = gemm2_tcgen05_kernel<BN, EPI>;
   static AttrOnce once;
   if (once.need()) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN);
+  const int tiles = ((M + C::BLOCK_M - 1) / C::BLOCK_M) * (N / BN) * (ep.ksplit > 1 ? ep.ksplit : 1);
   int pairs = g_num_sms / 2;
   if (t_opts->pair_limit > 0 && t_opts->pair_limit < pairs) pairs = t_opts->pair_limit;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -270,7 +270,11 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
   if ((EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_ACT_BF16) &&
       (!ep.stats || !ep.bias || ep.ln_slabs < 1 || ep.ln_slabs > 8 || ep.ln_slabs * LN_SLAB != K))
     return fail(MMCM_EINVAL, "gemm: EPI_LNFOLD needs stats, bias and K == 128 * slabs <= 1024");
-  if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
+  if (ep.ksplit > 1) {   // partial sums go to planes of a scratch buffer: plain TMA stores, no per-thread path
+    if (EPI != EPI_BIAS_RESID_F32 || !tma_out || ep.resid || (K / C::BLOCK_K) % ep.ksplit != 0 || ep.part_rows < M)
+      return fail(MMCM_EINVAL, "gemm: split-K needs the fp32 TMA-store epilogue, no residual and K / 64 %% ksplit == 0");
+    CKR(get_tmap(&tc, ep.out, (int64_t)ep.ksplit * ep.part_rows, ep.ldo, -2, false));
+  } else if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
   CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, td, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
   CK(cudaGetLastError());
   return MMCM_OK;
@@ -352,14 +356,24 @@ static int launch_gemm(const bf16* A, const bf16* W, int M, int N, int K, int ep
 }
 
 // ------------------------------------------------------------------------------------------------ other launchers
+// split-K partial sums waiting to be folded into a residual buffer by the next LayerNorm that reads it
+struct PendingParts {
+  const float* part = nullptr;
+  int ksplit = 0, part_rows = 0;
+};
+
 static int launch_layernorm(const float* x, const float* g, const float* b, float eps, int rows, int D,
                             const int* gather, bf16* out_bf16, float* out_f32, cudaStream_t st, LaunchStats* stats,
-                            const int* rows_dev = nullptr) {
+                            const int* rows_dev = nullptr, PendingParts* pend = nullptr) {
   if (rows <= 0) return MMCM_OK;
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
-  if (D == 512) CK(launch_k(layernorm_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
-  else if (D == 768) CK(launch_k(layernorm_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
-  else if (D == 1024) CK(launch_k(layernorm_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev));
+  const float* part = (pend && pend->part) ? pend->part : nullptr;
+  const int ks = part ? pend->ksplit : 0, pr = part ? pend->part_rows : 0;
+  float* xrw = part ? const_cast<float*>(x) : nullptr;
+  if (pend) *pend = PendingParts();
+  if (D == 512) CK(launch_k(layernorm_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev, part, ks, pr, xrw));
+  else if (D == 768) CK(launch_k(layernorm_kernel<768>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev, part, ks, pr, xrw));
+  else if (D == 1024) CK(launch_k(layernorm_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, g, b, eps, rows, gather, out_bf16, out_f32, rows_dev, part, ks, pr, xrw));
   else return fail(MMCM_EINVAL, "layernorm: unsupported width %d (512, 768, 1024)", D);
   CK(cudaGetLastError());
   if (stats) stats->launches++;
@@ -532,9 +546,14 @@ struct Arena {  // activations of one tower for one micro-batch
   bf16 *attp = nullptr, *hp = nullptr, *ffp = nullptr;
   // LN fold: per-row (sum, M2) of every 128-column slab of x / xp, written by the producer of the rows
   float2 *stats = nullptr, *statsp = nullptr;
+  // small forwards (B < 16): split-K partial sums of the residual GEMMs, kSplitPlanes planes of kSplitRows rows, and
+  // which of x / xp still has to absorb them (the next LayerNorm on that buffer does)
+  float* part = nullptr;
+  PendingParts pend_x, pend_xp;
   int64_t rows = 0;
   int mb = 0;
 };
+constexpr int kSplitPlanes = 4, kSplitRows = 1280;   // >= 15 samples x 77 tokens
 
 struct mmcm_handle_s {
   mmcm_config cfg;
@@ -602,6 +621,7 @@ struct mmcm_handle_s {
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   bool fold_forward = true;   // this forward runs the LN fold (opt_ln_fold and B >= kLnFoldMinBatch)
+  int opt_split_k = 1;        // small forwards: split-K residual GEMMs, partials absorbed by the following LayerNorm
   int opt_head_cluster = 1;   // B <= 144: the head kernel runs as clusters of 8 CTAs per 8 samples (heads.cuh)
   int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
   int last_chunk_text = 0, last_chunk_vis = 0;
@@ -860,7 +880,7 @@ static void free_arena(Eng* e, Arena& a) {
   dfree(e, a.x); dfree(e, a.h); dfree(e, a.qkv); dfree(e, a.att); dfree(e, a.ff); dfree(e, a.pool_row);
   dfree(e, a.seq_start); dfree(e, a.seq_len); dfree(e, a.rows_dev);
   dfree(e, a.xp); dfree(e, a.attp); dfree(e, a.hp); dfree(e, a.ffp);
-  dfree(e, a.stats); dfree(e, a.statsp);
+  dfree(e, a.stats); dfree(e, a.statsp); dfree(e, a.part);
   a = Arena();
 }
 static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) {
@@ -870,6 +890,8 @@ static int alloc_arena(Eng* e, Arena& a, const TowerW& t, int64_t rows, int mb) 
   CKR(dalloc(e, &a.statsp, (int64_t)mb * (t.D / LN_SLAB)));
   CK(cudaMemset(a.stats, 0, rows * (t.D / LN_SLAB) * sizeof(float2)));
   CK(cudaMemset(a.statsp, 0, (int64_t)mb * (t.D / LN_SLAB) * sizeof(float2)));
+  CKR(dalloc(e, &a.part, (int64_t)kSplitPlanes * kSplitRows * t.D));
+  CK(cudaMemset(a.part, 0, (int64_t)kSplitPlanes * kSplitRows * t.D * sizeof(float)));
   CKR(dalloc(e, &a.x, rows * t.D));
   CKR(dalloc(e, &a.h, rows * t.D));
   CKR(dalloc(e, &a.qkv, rows * 3 * t.D));
@@ -1035,14 +1057,32 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
       ep.stats = stats; ep.stats_pitch = pitch; ep.ln_slabs = D / LN_SLAB; ep.ln_eps = t.eps;
       return launch_gemm(h, W, M, N, D, act ? EPI_LNFOLD_ACT_BF16 : EPI_LNFOLD_BF16, ep, impl, st, S);
     }
-    CKR(launch_layernorm(x, nullptr, nullptr, t.eps, M, D, nullptr, h, nullptr, st, S, mdev));   // affine part lives in W / bias
+    // (affine part lives in W / bias; split-K partials of the residual GEMM in front are absorbed here)
+    CKR(launch_layernorm(x, nullptr, nullptr, t.eps, M, D, nullptr, h, nullptr, st, S, mdev, x == a.x ? &a.pend_x : &a.pend_xp));
     return launch_gemm(h, W, M, N, D, act ? EPI_BIAS_ACT_BF16 : EPI_BIAS_BF16, ep, impl, st, S);
   };
   // x += A @ W^T + b; with the fold also the bf16 copy and the slab statistics the next LN-consuming GEMM needs
   auto resid_linear = [&](const bf16* A, const bf16* W, const float* bias, float* x, bf16* xb, float2* stats, int pitch,
-                          int M, int K, const int* mdev, bool want_stats) -> int {
+                          int M, int K, const int* mdev, bool want_stats, bool ln_follows = true) -> int {
     EpiParams ep{};
     ep.bias = bias; ep.out = x; ep.resid = x; ep.ldo = D; ep.m_dev = mdev;
+    // Small forwards (B < 16, fold off): a handful of tiles, each CTA pair bound by the few KB it keeps in flight.
+    // Split K over idle pairs; the partial sums go to planes of a.part and the LayerNorm that follows adds them to x
+    // in a fixed order (deterministic, no reduction kernel, no inter-CTA waits).
+    if (!fold && ln_follows && impl == 0 && e->opt_split_k && e->opts.tma_epilogue && M <= kSplitRows) {
+      const int num_kb = K / 64;
+      const int bn = (M <= 256 && e->opts.narrow_tiles && D % 64 == 0) ? 64 : 256;
+      const int tiles = ((M + 255) / 256) * (D / bn);
+      int ks = std::min(kSplitPlanes, num_kb / 4);
+      while (ks > 1 && (num_kb % ks != 0 || tiles * ks > g_num_sms / 2)) --ks;
+      if (ks > 1) {
+        ep.out = a.part; ep.resid = nullptr; ep.ksplit = ks; ep.part_rows = kSplitRows;
+        CKR(launch_gemm(A, W, M, D, K, EPI_BIAS_RESID_F32, ep, impl, st, S));
+        PendingParts& pend = (x == a.x) ? a.pend_x : a.pend_xp;
+        pend.part = a.part; pend.ksplit = ks; pend.part_rows = kSplitRows;
+        return MMCM_OK;
+      }
+    }
     if (fold && want_stats) {
       ep.xb = xb; ep.stats = stats; ep.stats_pitch = pitch;
       return launch_gemm(A, W, M, D, K, EPI_RESID_STATS, ep, impl, st, S);
@@ -1070,7 +1110,8 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
     CKR(resid_linear(a.att, w.wo, w.bo, a.x, a.h, a.stats, (int)a.rows, rows, D, rdev, true));
     // ff = act(LN2(x) @ W1^T + b1); x = x + ff @ W2^T + b2     HF clip :381-384, :347-351
     CKR(ln_linear(a.x, a.h, a.stats, (int)a.rows, w.w1, w.b1, rows, F, a.ff, t.act, rdev));
-    CKR(resid_linear(a.ff, w.w2, w.b2, a.x, a.h, a.stats, (int)a.rows, rows, F, rdev, !last));
+    // (after the last layer the final LayerNorm may read only the pooled rows: keep x itself complete there)
+    CKR(resid_linear(a.ff, w.w2, w.b2, a.x, a.h, a.stats, (int)a.rows, rows, F, rdev, !last, !last));
   }
   return MMCM_OK;
 }
@@ -1114,8 +1155,9 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
   e->opts.pair_limit = 0;
   CKR(rl);
   // pooled = final_layer_norm(x)[pool_row]   (LayerNorm is row-wise, so only the pooled rows are normalised)
-  if (pl) CKR(launch_layernorm(a.xp, e->tfin_g, e->tfin_b, t.eps, n, t.D, nullptr, nullptr, pooled, st, &e->stats));
-  else CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats));
+  if (pl) CKR(launch_layernorm(a.xp, e->tfin_g, e->tfin_b, t.eps, n, t.D, nullptr, nullptr, pooled, st, &e->stats, nullptr, &a.pend_xp));
+  else CKR(launch_layernorm(a.x, e->tfin_g, e->tfin_b, t.eps, n, t.D, a.pool_row, nullptr, pooled, st, &e->stats, nullptr, &a.pend_x));
+  if (a.pend_x.part || a.pend_xp.part) return fail(MMCM_ESTATE, "internal: split-K partial sums of the text tower were not absorbed");
   e->last_text_rows = rows;
   return MMCM_OK;
 }
@@ -1180,12 +1222,12 @@ static int run_vision(Eng* e, const Pixels& px, int n, float* pooled, cudaStream
   e->opts.pair_limit = 0;
   CKR(rl);
   if (clip) {
-    if (pl) CKR(launch_layernorm(a.xp, e->post_g, e->post_b, t.eps, n, D, nullptr, nullptr, pooled, st, S));
-    else CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S));
+    if (pl) CKR(launch_layernorm(a.xp, e->post_g, e->post_b, t.eps, n, D, nullptr, nullptr, pooled, st, S, nullptr, &a.pend_xp));
+    else CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, n, D, a.pool_row, nullptr, pooled, st, S, nullptr, &a.pend_x));
   } else {
     // post_layernorm over all tokens, then the MAP head   HF siglip :617-649
     const int impl = e->opt_gemm_impl;
-    CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, rows, D, nullptr, a.h, nullptr, st, S));
+    CKR(launch_layernorm(a.x, e->post_g, e->post_b, t.eps, rows, D, nullptr, a.h, nullptr, st, S, nullptr, &a.pend_x));
     ep = EpiParams{};
     ep.bias = e->map_bkv; ep.out = e->map_kv; ep.ldo = 2 * D;
     CKR(launch_gemm(a.h, e->map_wkv, rows, 2 * D, D, EPI_BIAS_BF16, ep, impl, st, S));
@@ -1204,6 +1246,7 @@ static int run_vision(Eng* e, const Pixels& px, int n, float* pooled, cudaStream
     ep.bias = e->map_b2; ep.out = pooled; ep.resid = e->map_y; ep.ldo = D;
     CKR(launch_gemm(e->map_ff, e->map_w2, n, D, t.F, EPI_BIAS_RESID_F32, ep, impl, st, S));
   }
+  if (a.pend_x.part || a.pend_xp.part) return fail(MMCM_ESTATE, "internal: split-K partial sums of the vision tower were not absorbed");
   e->last_vis_rows = rows;
   return MMCM_OK;
 }
@@ -1978,6 +2021,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   }
   else if (n == "ln_fold") h->opt_ln_fold = value != 0;
   else if (n == "head_cluster") h->opt_head_cluster = value != 0;
+  else if (n == "split_k") h->opt_split_k = value != 0;
   else if (n == "narrow_tiles") h->opts.narrow_tiles = value != 0;
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;

@@ -13,13 +13,17 @@ namespace mmcm {
 //   gather   optional row indices (pooling: only the EOS / CLS rows are normalised) else row i
 //   out_bf16 optional bf16 [rows, D]  (operand of the next GEMM)
 //   out_f32  optional fp32 [rows, D]  (may alias x when gather == nullptr: pre_layrnorm in place)
+//   part     optional split-K partial sums of the residual GEMM in front of this LayerNorm (gemm2_tcgen05.cuh,
+//            EpiParams::ksplit): x_new = ((x + part[0]) + part[1]) + ... in this fixed order, written back to x_rw
+//            before it is normalised -- the reduction of a split-K GEMM without a reduction kernel or inter-CTA waits
 // One warp per row; D/128 float4 per lane held in registers (two-pass mean/variance, no re-read).
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float eps, const int rows_host, const int* __restrict__ gather,
-                 __nv_bfloat16* __restrict__ out_bf16, float* out_f32, const int* __restrict__ rows_dev) {
+                 __nv_bfloat16* __restrict__ out_bf16, float* out_f32, const int* __restrict__ rows_dev,
+                 const float* __restrict__ part, const int ksplit, const int part_rows, float* x_rw) {
   constexpr int V = D / 128;  // float4 per lane
   pdl_trigger();
   pdl_wait();
@@ -28,14 +32,28 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int src = gather ? gather[warp] : warp;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)src * D);
+  // (with partial sums the row is read through the pointer it is rewritten through, not the __restrict__ one)
+  const float4* xr = part ? reinterpret_cast<const float4*>(x_rw + (size_t)src * D)
+                          : reinterpret_cast<const float4*>(x + (size_t)src * D);
   float4 v[V];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  if (part) {
+    for (int k = 0; k < ksplit; ++k) {
+      const float4* pr = reinterpret_cast<const float4*>(part + ((size_t)k * part_rows + src) * D);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float4 p = pr[lane + 32 * i];
+        v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+      }
+    }
+    float4* xw = reinterpret_cast<float4*>(x_rw + (size_t)src * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) xw[lane + 32 * i] = v[i];
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll

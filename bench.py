@@ -220,7 +220,7 @@ def torch_gpu_comparator(model, a, batch, steps):
 
 def h2d_probe(dev, world, nbytes=256 << 20, reps=6):
     """Pinned host -> device copy bandwidth of this rank while ALL ranks copy at once (GB/s): the ceiling of the e2e
-    leg's fp32 pixel stream on this box.  Returns (this rank's GB/s, aggregate GB/s)."""
+    leg's fp32 pixel stream on this box.  Returns (this rank's GB/s, aggregate GB/s, slowest rank's GB/s)."""
     import torch
     import torch.distributed as dist
     h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -237,9 +237,11 @@ def h2d_probe(dev, world, nbytes=256 << 20, reps=6):
     torch.cuda.synchronize()
     gbs = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
     t = torch.tensor([gbs], device=dev)
+    lo = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return gbs, t.item()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return gbs, t.item(), lo.item()
 
 
 def parity_gate(logits, ref):
@@ -450,6 +452,7 @@ def main():
                                                         pinned["image_present"], out=out_h))
         e2e = {"value": v, "unit": "samples/s",
                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 5 * 4, "steps": ksteps,
+               "copy_share_of_call": eng.last_host_copy_share(),
                "api": "mmcm_forward_host (pinned host buffers, chunked H2D overlapped with the towers)"}
         # the same call on raw uint8 HWC images: ToTensor + Normalize inside the im2col
         img_u8 = torch.randint(0, 256, (B, a.image, a.image, 3), dtype=torch.uint8,
@@ -466,18 +469,20 @@ def main():
                                    "run inside the patch im2col, logits bit-identical to the fp32-pixel call)"}
 
         # what the box can deliver to all GPUs at once: the ceiling of the fp32-pixel e2e leg above
-        mine, agg = h2d_probe(dev, world)
-        bound = agg * 1e9 / (in_bytes / B)
+        mine, agg, slowest = h2d_probe(dev, world)
+        # every step is timed as the max over ranks, so the slowest rank's link sets the ceiling
+        bound = world * slowest * 1e9 / (in_bytes / B)
         e2e["frac_of_h2d_ceiling"] = e2e["value"] / bound
         e2e["frac_of_device_resident"] = e2e["value"] / value
         if e2e["value"] > 0.75 * bound:
-            e2e["bound_by"] = ("host->device bandwidth of this box: all ranks together move "
-                               f"{agg:.0f} GB/s of pinned memory ({mine:.1f} GB/s on this rank), the fp32 pixel_values "
+            e2e["bound_by"] = ("host->device bandwidth of this box: with all ranks copying pinned memory at once the "
+                               f"slowest rank gets {slowest:.1f} GB/s ({agg:.0f} GB/s in total), the fp32 pixel_values "
                                f"contract needs {value / world * (in_bytes / B) / 1e9:.1f} GB/s per GPU at the device-resident rate")
         e2e["h2d_ceiling"] = {"pinned_h2d_gbs_this_rank": mine, "pinned_h2d_gbs_all_ranks": agg,
-                              "samples_per_s_bound": bound,
-                              "note": "all ranks copy 256 MiB pinned buffers concurrently (CUDA events); bound = aggregate "
-                                      "bandwidth / input bytes per sample of the reference's fp32 pixel_values contract"}
+                              "pinned_h2d_gbs_slowest_rank": slowest, "samples_per_s_bound": bound,
+                              "note": "all ranks copy 256 MiB pinned buffers concurrently (CUDA events); bound = n_gpus x "
+                                      "slowest rank's bandwidth / input bytes per sample of the reference's fp32 "
+                                      "pixel_values contract (steps are timed as the max over ranks)"}
 
     # ------------------------------------------------------------------ BASELINE config 5: one 22.5 k-sample scoring job
     if world > 1 and not args.no_e2e:

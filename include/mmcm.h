@@ -137,6 +137,10 @@ MMCM_API int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t
                    void* stream);
 /* Number of kernels this library launched during the last mmcm_forward on this handle. */
 MMCM_API int64_t mmcm_last_launch_count(mmcm_handle h);
+/* Share of the last mmcm_forward_host* call's wall time during which its pixel copies were still running (CUDA events).
+ * Above 0.85 the call was bound by host->device bandwidth; the next call then tapers its last H2D stages (cv, ..., cv/2,
+ * cv/4, cv/4) so that little tower work is left when the last bytes land. */
+MMCM_API double mmcm_last_host_copy_share(mmcm_handle h);
 /* Samples per internal pass (micro-batch) the last forward used for the text and the vision tower. */
 MMCM_API int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* vision_chunk_out);
 /* CUDA-event time (ms) of the GEMM launches of the last forward when profiling was enabled with

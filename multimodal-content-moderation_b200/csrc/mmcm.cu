@@ -553,7 +553,7 @@ struct Arena {  // activations of one tower for one micro-batch
   int64_t rows = 0;
   int mb = 0;
 };
-constexpr int kSplitPlanes = 4, kSplitRows = 1280;   // >= 15 samples x 77 tokens
+constexpr int kSplitPlanes = 4, kSplitRows = 3072;   // >= 15 samples x 197 tokens (the largest forward that splits)
 
 struct mmcm_handle_s {
   mmcm_config cfg;
@@ -609,6 +609,9 @@ struct mmcm_handle_s {
 
   cudaStream_t s_text = nullptr, s_vis = nullptr, s_copy = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_text = nullptr, ev_vis = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_copy_end = nullptr, ev_end = nullptr;   // timed: what bounded the last host call
+  bool h2d_bound = false;
+  float last_h2d_share = 0.f;
   std::vector<cudaEvent_t> ev_chunk;
   // options
   // CUDA graphs of whole forwards for small batches (launch-bound regime): key = (B, S, mask?, probs?)
@@ -621,6 +624,7 @@ struct mmcm_handle_s {
   int opt_varlen_text = 1;   // CLIP text: keep only the rows up to the pooled (EOS) position -- exact, see rowwise.cuh
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   bool fold_forward = true;   // this forward runs the LN fold (opt_ln_fold and B >= kLnFoldMinBatch)
+  bool split_forward = false; // this forward splits K in its residual GEMMs (B < kLnFoldMinBatch, see run_layers)
   int opt_split_k = 1;        // small forwards: split-K residual GEMMs, partials absorbed by the following LayerNorm
   int opt_head_cluster = 1;   // B <= 144: the head kernel runs as clusters of 8 CTAs per 8 samples (heads.cuh)
   int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
@@ -1069,12 +1073,12 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
     // Small forwards (B < 16, fold off): a handful of tiles, each CTA pair bound by the few KB it keeps in flight.
     // Split K over idle pairs; the partial sums go to planes of a.part and the LayerNorm that follows adds them to x
     // in a fixed order (deterministic, no reduction kernel, no inter-CTA waits).
-    if (!fold && ln_follows && impl == 0 && e->opt_split_k && e->opts.tma_epilogue && M <= kSplitRows) {
+    // The split count depends on K only, never on M: every row of a forward -- whatever micro-batch it travels in, and
+    // in the pooled-rows last layer as much as in the all-rows one -- sees the same summation order.
+    if (!fold && ln_follows && impl == 0 && e->split_forward && M <= kSplitRows) {
       const int num_kb = K / 64;
-      const int bn = (M <= 256 && e->opts.narrow_tiles && D % 64 == 0) ? 64 : 256;
-      const int tiles = ((M + 255) / 256) * (D / bn);
       int ks = std::min(kSplitPlanes, num_kb / 4);
-      while (ks > 1 && (num_kb % ks != 0 || tiles * ks > g_num_sms / 2)) --ks;
+      while (ks > 1 && num_kb % ks != 0) --ks;
       if (ks > 1) {
         ep.out = a.part; ep.resid = nullptr; ep.ksplit = ks; ep.part_rows = kSplitRows;
         CKR(launch_gemm(A, W, M, D, K, EPI_BIAS_RESID_F32, ep, impl, st, S));
@@ -1103,7 +1107,9 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
       S->launches++;
       CKR(resid_linear(a.attp, w.wo, w.bo, a.xp, a.hp, a.statsp, a.mb, B, D, nullptr, true));
       CKR(ln_linear(a.xp, a.hp, a.statsp, a.mb, w.w1, w.b1, B, F, a.ffp, t.act, nullptr));
-      CKR(resid_linear(a.ffp, w.w2, w.b2, a.xp, nullptr, nullptr, 0, B, F, nullptr, false));   // the final LN reads x itself
+      // (the final LN reads x itself; no split-K here: the all-rows path keeps its last fc2 unsplit so that x stays
+      // complete for every row, and the two paths must add in the same order to stay bit-identical)
+      CKR(resid_linear(a.ffp, w.w2, w.b2, a.xp, nullptr, nullptr, 0, B, F, nullptr, false, false));
       break;
     }
     // x = x + att @ Wo^T + bo                                  HF clip :334, :379
@@ -1335,6 +1341,8 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
   clear_gemm_events(e->stats);
   if (B == 0) return MMCM_OK;
   e->fold_forward = e->opt_ln_fold && B >= kLnFoldMinBatch;
+  e->split_forward = e->opt_split_k && e->opts.tma_epilogue && B < kLnFoldMinBatch &&
+                     (int64_t)B * std::max(e->cfg.max_pos, vis_tokens(e->cfg)) <= kSplitRows;
   const int ct = e->opt_auto_chunk ? choose_chunk(e->text, S, B, e->opt_micro_batch, g_num_sms) : std::min(B, e->opt_micro_batch);
   const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, e->opt_micro_batch, g_num_sms)
                                    : std::min(B, e->opt_micro_batch);
@@ -1414,6 +1422,9 @@ int mmcm_create(const mmcm_config* cfg, int device, mmcm_handle* out) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_text, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_vis, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_t0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_copy_end);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_end);
     if (ce != cudaSuccess) r = fail(MMCM_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
   }
   if (r != MMCM_OK) {
@@ -1443,6 +1454,9 @@ int mmcm_destroy(mmcm_handle h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_text) cudaEventDestroy(h->ev_text);
   if (h->ev_vis) cudaEventDestroy(h->ev_vis);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_copy_end) cudaEventDestroy(h->ev_copy_end);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
   for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
   delete h;
   return MMCM_OK;
@@ -1815,6 +1829,8 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   if (B == 0) return MMCM_OK;
   OptsScope scope(&e->opts);
   e->fold_forward = e->opt_ln_fold && B >= kLnFoldMinBatch;
+  e->split_forward = e->opt_split_k && e->opts.tma_epilogue && B < kLnFoldMinBatch &&
+                     (int64_t)B * std::max(e->cfg.max_pos, vis_tokens(e->cfg)) <= kSplitRows;
   const mmcm_config& c = e->cfg;
   const size_t px_bytes = hpx.bytes_per_sample(c);
   const char* hsrc = hpx.u8 ? reinterpret_cast<const char*>(hpx.u8) : reinterpret_cast<const char*>(hpx.f32);
@@ -1839,20 +1855,39 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   e->last_chunk_text = ct; e->last_chunk_vis = cv;
   CKR(ensure_arenas(e, ct, cv));
   CKR(ensure_batch(e, B));
-  const int nchunks = (B + cv - 1) / cv;
+  // Stage schedule.  When the copy stream is the bottleneck (N ranks sharing a host that cannot feed N x 32 GB/s: the
+  // copies of the previous call took > 85 % of its time) the step is "all copies, then the towers of the LAST stage":
+  // taper the last stages (cv, ..., cv/2, cv/4, cv/4) so that little work is left when the last bytes land.  When the
+  // towers are the bottleneck equal stages are better (fewer, fuller GEMM rounds), so the schedule follows what the
+  // previous call measured (8 GPUs, 23 GB/s per rank: 287 k -> see profiles/r02_bench_8gpu*.json).
+  std::vector<int> stages;
+  {
+    int left = B;
+    const bool taper = e->h2d_bound && e->opt_host_chunk == 0 && B >= 2 * cv;
+    while (left > 0) {
+      int n = std::min(cv, left);
+      if (taper && left <= cv + cv / 2) n = (left > cv / 3) ? std::max(cv / 4, (left + 1) / 2) : left;
+      n = std::min(n, left);
+      stages.push_back(n);
+      left -= n;
+    }
+  }
+  const int nchunks = (int)stages.size();
   while ((int)e->ev_chunk.size() < nchunks) {
     cudaEvent_t ev;
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev_chunk.push_back(ev);
   }
   CK(cudaEventRecord(e->ev_fork, st));
+  CK(cudaEventRecord(e->ev_t0, st));
   CK(cudaStreamWaitEvent(e->s_copy, e->ev_fork, 0));
-  for (int ci = 0; ci < nchunks; ++ci) {
-    const int b0 = ci * cv, n = std::min(cv, (int)B - b0);
+  for (int ci = 0, b0 = 0; ci < nchunks; b0 += stages[ci], ++ci) {
+    const int n = stages[ci];
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(e->d_px) + b0 * px_bytes, hsrc + b0 * px_bytes, (size_t)n * px_bytes,
                        cudaMemcpyHostToDevice, e->s_copy));
     CK(cudaEventRecord(e->ev_chunk[ci], e->s_copy));
   }
+  CK(cudaEventRecord(e->ev_copy_end, e->s_copy));
   e->stats.launches = 0;
   clear_gemm_events(e->stats);
   CK(cudaStreamWaitEvent(e->s_text, e->ev_fork, 0));
@@ -1866,7 +1901,7 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
       bt += n;
     }
     if (bv < B) {
-      const int n = std::min(cv, (int)B - bv);
+      const int n = stages[ci];
       CK(cudaStreamWaitEvent(e->s_vis, e->ev_chunk[ci], 0));
       CKR(run_vision(e, dpx.at(bv, c), n, e->pooled_v + (int64_t)bv * c.vis_hidden, e->s_vis));
       bv += n;
@@ -1881,7 +1916,19 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   e->last_B = B;
   CK(cudaMemcpyAsync(logits_out, e->d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
   if (probs_out) CK(cudaMemcpyAsync(probs_out, e->d_probs, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(e->ev_end, st));
   CK(cudaStreamSynchronize(st));
+  {  // what bounded this call: the copy stream's share of the wall time (hysteresis: on above 85 %, off below 70 %)
+    float copy_ms = 0.f, total_ms = 0.f;
+    if (cudaEventElapsedTime(&copy_ms, e->ev_t0, e->ev_copy_end) == cudaSuccess &&
+        cudaEventElapsedTime(&total_ms, e->ev_t0, e->ev_end) == cudaSuccess && total_ms > 0.f) {
+      e->last_h2d_share = copy_ms / total_ms;
+      if (e->last_h2d_share > 0.85f) e->h2d_bound = true;
+      else if (e->last_h2d_share < 0.70f) e->h2d_bound = false;
+    } else {
+      cudaGetLastError();
+    }
+  }
   return MMCM_OK;
 }
 
@@ -1937,6 +1984,8 @@ int mmcm_get_stage(mmcm_handle h, const char* name, float* dst, int64_t capacity
 }
 
 int64_t mmcm_last_launch_count(mmcm_handle h) { return h ? h->stats.launches : 0; }
+
+double mmcm_last_host_copy_share(mmcm_handle h) { return h ? (double)h->last_h2d_share : 0.0; }
 
 int mmcm_last_chunks(mmcm_handle h, int32_t* text_chunk_out, int32_t* vision_chunk_out) {
   if (!h) return fail(MMCM_EINVAL, "null handle");

@@ -234,6 +234,10 @@ class Engine:
     def last_launch_count(self) -> int:
         return int(self.lib.mmcm_last_launch_count(self._h))
 
+    def last_host_copy_share(self) -> float:
+        """Share of the last forward_host* call during which its H2D pixel copies were running (> 0.85: H2D bound)."""
+        return float(self.lib.mmcm_last_host_copy_share(self._h))
+
     def last_chunks(self):
         """(text, vision) micro-batch sizes the last forward split the batch into."""
         t, v = C.c_int32(0), C.c_int32(0)

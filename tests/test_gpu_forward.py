@@ -309,7 +309,8 @@ def test_small_forward_split_k_matches_unsplit(name):
             y1 = m(**d)["logits"].cpu()
             assert torch.equal(m(**d)["logits"].cpu(), y1)                       # deterministic
             # (another fp32 summation order flips some bf16 roundings downstream: bf16-noise level, ~0.2 % of the std)
-            assert (y1 - y0).abs().max().item() <= 1e-2 * max(ref.std().item(), 1.0), f"B={B} pooled={pooled}"
+            tol = 0.5 * REL_GATE[_gate_key(kind, a)] * max(ref.std().item(), 1.0)
+            assert (y1 - y0).abs().max().item() <= tol, f"B={B} pooled={pooled}: {(y1 - y0).abs().max().item()} > {tol}"
             err = (y1 - ref).abs().max().item()
             assert err <= REL_GATE[_gate_key(kind, a)] * 3.3, f"B={B} pooled={pooled}: {err}"
     m.set_option("pooled_last_layer", 1)

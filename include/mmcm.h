@@ -265,6 +265,21 @@ MMCM_API int mmcm_resize_crop_u8(const uint8_t* src, const int64_t* offsets, con
 MMCM_API int mmcm_postprocess(const float* logits, const float* thresholds, const float* labels, int32_t B, int32_t C,
                               float* probs_out, uint8_t* decisions_out, uint8_t* any_out, uint64_t* confusion_accum,
                               void* stream);
+/* --- CLIP tokenizer, host side: the step that produces input_ids / attention_mask --------------
+ * Replaces `tokenizer(text, padding="max_length", truncation=True, max_length=77, return_attention_mask=True)` of
+ * R/src/data/dataset.py:148-165 / R/scripts/inference.py:168-180 for the CLIP backends, i.e. the pipeline Hugging Face's
+ * CLIPTokenizer configures (HF/models/clip/tokenization_clip.py:68-118): special tokens cut out of the raw text; NFC,
+ * white-space runs -> ' ', Unicode lower-casing; Split on 's|'t|'re|'ve|'m|'ll|'d|\p{L}+|\p{N}|[^\s\p{L}\p{N}]+;
+ * byte-level BPE with "</w>"; [bos] ... [eos], truncation, padding with "<|endoftext|>".  vocab.json / merges.txt are the
+ * checkpoint's own files (none ship here).  texts[i] is UTF-8, lengths[i] its byte length (no terminator needed);
+ * outputs are HOST int64 [n, max_len].  n_threads <= 0: all hardware threads.  Thread-safe for concurrent encodes. */
+typedef struct mmcm_tokenizer_s* mmcm_tokenizer;
+MMCM_API int mmcm_tokenizer_create(const char* vocab_json_path, const char* merges_txt_path, mmcm_tokenizer* out);
+MMCM_API int mmcm_tokenizer_destroy(mmcm_tokenizer t);
+MMCM_API int mmcm_tokenizer_info(mmcm_tokenizer t, int32_t* vocab_size, int32_t* bos_id, int32_t* eos_id, int32_t* pad_id);
+MMCM_API int mmcm_tokenizer_encode(mmcm_tokenizer t, const char* const* texts, const int64_t* lengths, int32_t n,
+                                   int32_t max_len, int64_t* input_ids_out, int64_t* attention_mask_out,
+                                   int32_t n_threads);
 /* Dev tool: when device_buffer != NULL, mmcm_gemm_bf16 (impl 0) writes 16 clock64 stamps per CTA into it
  * (>= 148 * 16 int64); NULL switches tracing off. */
 MMCM_API int mmcm_debug_set_gemm_trace(void* device_buffer);

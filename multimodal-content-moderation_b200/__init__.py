@@ -12,7 +12,8 @@ from . import arch, build, checkpoint, lib, prepost, sharding, synthetic  # noqa
 from .engine import Engine  # noqa: F401
 from .checkpoint import PackedScorer, load_checkpoint  # noqa: F401
 from .pipeline import BatchedScorer  # noqa: F401
+from .tokenizer import ClipTokenizer  # noqa: F401
 from .modules import FocalWithLogitsLoss, MultiModalFusionClassifier, MultiTaskClassifier  # noqa: F401
 
-__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "BatchedScorer", "PackedScorer", "load_checkpoint", "arch", "build",
+__all__ = ["MultiModalFusionClassifier", "MultiTaskClassifier", "FocalWithLogitsLoss", "Engine", "BatchedScorer", "ClipTokenizer", "PackedScorer", "load_checkpoint", "arch", "build",
            "checkpoint", "lib", "prepost", "sharding", "synthetic"]

@@ -42,6 +42,7 @@
 #include "heads.cuh"
 #include "prepost.cuh"
 #include "rowwise.cuh"
+#include "tokenizer.h"
 
 using namespace mmcm;
 typedef __nv_bfloat16 bf16;
@@ -2240,6 +2241,45 @@ int mmcm_postprocess(const float* logits, const float* thresholds, const float* 
   CK(launch_k(postprocess_kernel, dim3((B + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), logits,
               thresholds, labels, B, C, probs_out, decisions_out, any_out,
               reinterpret_cast<unsigned long long*>(confusion_accum)));
+  return MMCM_OK;
+}
+
+// ---------------------------------------------------------------------------------- CLIP tokenizer (host)
+struct mmcm_tokenizer_s {
+  mmcm_tok::ClipTokenizer tok;
+};
+
+int mmcm_tokenizer_create(const char* vocab_json_path, const char* merges_txt_path, mmcm_tokenizer* out) {
+  if (!vocab_json_path || !merges_txt_path || !out) return fail(MMCM_EINVAL, "null argument");
+  *out = nullptr;
+  std::unique_ptr<mmcm_tokenizer_s> t(new mmcm_tokenizer_s());
+  const std::string err = t->tok.load(vocab_json_path, merges_txt_path);
+  if (!err.empty()) return fail(MMCM_EINVAL, "tokenizer: %s", err.c_str());
+  *out = t.release();
+  return MMCM_OK;
+}
+
+int mmcm_tokenizer_destroy(mmcm_tokenizer t) {
+  delete t;
+  return MMCM_OK;
+}
+
+int mmcm_tokenizer_info(mmcm_tokenizer t, int32_t* vocab_size, int32_t* bos_id, int32_t* eos_id, int32_t* pad_id) {
+  if (!t) return fail(MMCM_EINVAL, "null tokenizer");
+  if (vocab_size) *vocab_size = t->tok.vocab_size();
+  if (bos_id) *bos_id = t->tok.bos();
+  if (eos_id) *eos_id = t->tok.eos();
+  if (pad_id) *pad_id = t->tok.eos();     // CLIP pads with "<|endoftext|>"
+  return MMCM_OK;
+}
+
+int mmcm_tokenizer_encode(mmcm_tokenizer t, const char* const* texts, const int64_t* lengths, int32_t n, int32_t max_len,
+                          int64_t* input_ids_out, int64_t* attention_mask_out, int32_t n_threads) {
+  if (!t || (n > 0 && (!texts || !lengths || !input_ids_out || !attention_mask_out))) return fail(MMCM_EINVAL, "null argument");
+  if (n < 0 || max_len < 2) return fail(MMCM_EINVAL, "tokenizer: need n >= 0 and max_len >= 2");
+  for (int i = 0; i < n; ++i)
+    if (!texts[i] || lengths[i] < 0) return fail(MMCM_EINVAL, "tokenizer: text %d is null or has a negative length", i);
+  mmcm_tok::encode_batch(t->tok, texts, lengths, n, max_len, input_ids_out, attention_mask_out, n_threads);
   return MMCM_OK;
 }
 

@@ -61,6 +61,12 @@ _SIGS = {
     "mmcm_prep_rows": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_gemm_resid_stats": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "mmcm_gemm_lnfold": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),
+    "mmcm_tokenizer_create": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(_P)]),
+    "mmcm_tokenizer_destroy": (C.c_int, [_P]),
+    "mmcm_tokenizer_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]),
+    "mmcm_tokenizer_encode": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, _P, _P,
+                                        C.c_int32]),
     "mmcm_layernorm": (C.c_int, [_P, _P, _P, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mmcm_cast_bf16": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P]),

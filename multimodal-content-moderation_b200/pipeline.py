@@ -20,7 +20,7 @@ from . import prepost
 class BatchedScorer:
     def __init__(self, model: torch.nn.Module, class_names: Sequence[str], thresholds: Sequence[float],
                  image_mean: Optional[Sequence[float]] = None, image_std: Optional[Sequence[float]] = None,
-                 max_batch: int = 1024):
+                 max_batch: int = 1024, tokenizer=None, max_text_length: Optional[int] = None):
         """image_mean / image_std default to the image processor constants of the model's encoder family (CLIP's
         dataset statistics, 0.5 / 0.5 for SigLIP) -- what `img_processor.image_mean` gives the reference's transform
         (R/src/data/dataset.py:100-110)."""
@@ -38,6 +38,20 @@ class BatchedScorer:
         if self.thresholds.numel() != len(self.class_names):
             raise ValueError("one threshold per class is required")      # inference.py:118-121 pads/validates likewise
         self.mean, self.std, self.max_batch = list(image_mean), list(image_std), int(max_batch)
+        # optional: anything callable like the reference's tokenizer (tokenizer.ClipTokenizer, or the HF object itself)
+        self.tokenizer = tokenizer
+        self.max_text_length = int(max_text_length or model._arch.max_pos)
+
+    def score_texts(self, texts: Sequence[str], images_u8=None, image_present: Optional[torch.Tensor] = None
+                    ) -> Dict[str, torch.Tensor]:
+        """Raw request texts in: tokenised the way the reference does (pad to max_length, truncation,
+        R/scripts/inference.py:168-180), `text_present` = non-blank text (inference.py:201), then `score`."""
+        if self.tokenizer is None:
+            raise RuntimeError("BatchedScorer was built without a tokenizer")
+        enc = self.tokenizer(list(texts), padding="max_length", truncation=True, max_length=self.max_text_length,
+                             return_attention_mask=True, return_tensors="pt")
+        tp = torch.tensor([1.0 if (t and t.strip()) else 0.0 for t in texts], dtype=torch.float32)
+        return self.score(enc["input_ids"], enc["attention_mask"], images_u8, text_present=tp, image_present=image_present)
 
     @torch.no_grad()
     def score(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, images_u8: Optional[torch.Tensor],

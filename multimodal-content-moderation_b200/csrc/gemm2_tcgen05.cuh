@@ -457,6 +457,25 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
           const int row = row_base + lane;
           if (row < M) ep.stats[(size_t)(col_base / LN_SLAB) * ep.stats_pitch + row] = make_float2(run_s, run_m2);
+        } else if (!kF32 && HALF_N == 32) {
+          // 64-column tiles (single-row-block GEMMs): one 32-column chunk per warp, staged as a 32 x 64 B tile with the
+          // 64B swizzle (16-byte slot i of row r sits at slot i ^ ((r >> 1) & 3)) and stored by TMA
+          uint32_t r[32], w[16];
+          tmem_ld32(t_row, r);
+          tmem_ld_wait();
+          epi_pack_bf16<EPI>(ep, bias_smem, r, w, ln_rs);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          const uint32_t bt = stage_smem + lane * 64;
+          const uint32_t sw2 = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(bt + ((i ^ sw2) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, stage_smem, col_base, row_base);
+            bulk_commit();
+          }
         } else if (!kF32) {
 #pragma unroll 1
           for (int c = 0; c < HALF_N / 64; ++c) {

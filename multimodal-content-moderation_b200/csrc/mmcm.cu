@@ -275,7 +275,9 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Ep
     if (EPI != EPI_BIAS_RESID_F32 || !tma_out || ep.resid || (K / C::BLOCK_K) % ep.ksplit != 0 || ep.part_rows < M)
       return fail(MMCM_EINVAL, "gemm: split-K needs the fp32 TMA-store epilogue, no residual and K / 64 %% ksplit == 0");
     CKR(get_tmap(&tc, ep.out, (int64_t)ep.ksplit * ep.part_rows, ep.ldo, -2, false));
-  } else if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : -1, false));
+  } else if (tma_out) CKR(get_tmap(&tc, ep.out, M, ep.ldo, f32 ? -2 : (BN == 64 ? -3 : -1), false));
+  if (BN == 64 && !f32 && EPI != EPI_PATCH_F32 && !tma_out)
+    return fail(MMCM_EINVAL, "gemm: 64-column bf16 tiles need the TMA-store epilogue");
   CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, tc, td, ep, M, N, K, tma_out));   // __cluster_dims__(2,1,1)
   CK(cudaGetLastError());
   return MMCM_OK;
@@ -300,18 +302,22 @@ static int launch_gemm_epi(const bf16* A, const bf16* W, int M, int N, int K, co
   int BN = (N % 256 == 0) ? 256 : 128;
   // One row block (M <= 256: the online B = 1 path, the pooled-rows last layer): a 256-wide tile leaves N / 256 = 2-3
   // CTA pairs streaming the whole weight matrix while 140 SMs idle -- fc2 took 20 us at B = 1, bound by what two SMs
-  // pull from L2 (tools/b1_launches.py).  Narrow tiles spread the weight stream: 64 columns for the fp32 epilogues
-  // (one 32-column chunk per epilogue warp), 128 for the bf16 ones.  The per-element k order is unchanged.
+  // pull from L2 (tools/b1_launches.py).  Narrow tiles spread the weight stream: 64 columns (one 32-column chunk per
+  // epilogue warp; 128 for bf16 outputs without the TMA-store epilogue).  The per-element k order is unchanged.
   if (impl == 0 && M <= 256 && t_opts->narrow_tiles) {
     if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32) { if (N % 64 == 0) BN = 64; }
-    else if constexpr (!kPairOnly) { if (N % 128 == 0) BN = 128; }
+    else if constexpr (!kPairOnly) {
+      const bool tma_ok = t_opts->tma_epilogue && (ep.ldo * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+      if (N % 64 == 0 && tma_ok) BN = 64;          // the 64-column bf16 epilogue exists as a TMA store only
+      else if (N % 128 == 0) BN = 128;
+    }
   }
   CUtensorMap ta, tb;
   CKR(get_tmap(&ta, A, M, K, 128, false));
   if (impl == 0) {  // CTA-pair kernel: every CTA stages half of the B tile
     CKR(get_tmap(&tb, W, N, K, BN / 2, true));
     if (BN == 256) return launch_tc_pair<256, EPI>(ta, tb, ep, M, N, K, st);
-    if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_PATCH_F32)
+    if constexpr (!kPairOnly)
       if (BN == 64) return launch_tc_pair<64, EPI>(ta, tb, ep, M, N, K, st);
     if constexpr (!kPairOnly) return launch_tc_pair<128, EPI>(ta, tb, ep, M, N, K, st);
   }

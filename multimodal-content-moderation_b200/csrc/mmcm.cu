@@ -632,6 +632,7 @@ struct mmcm_handle_s {
   int opt_streams = 2, opt_gemm_impl = 0, opt_micro_batch = 1024, opt_debug_feats = 0, opt_auto_chunk = 1;
   bool fold_forward = true;   // this forward runs the LN fold (opt_ln_fold and B >= kLnFoldMinBatch)
   bool split_forward = false; // this forward splits K in its residual GEMMs (B < kLnFoldMinBatch, see run_layers)
+  int opt_skip_absent = 1;    // packed text: samples whose text cannot reach the logits keep one row (text_plan_kernel)
   int opt_split_k = 1;        // small forwards: split-K residual GEMMs, partials absorbed by the following LayerNorm
   int opt_head_cluster = 1;   // B <= 144: the head kernel runs as clusters of 8 CTAs per 8 samples (heads.cuh)
   int opt_ln_fold = 1;        // LayerNorm folded into the residual / consumer GEMMs (gemm_impl 0 only), else a separate pass
@@ -1129,7 +1130,8 @@ static int run_layers(Eng* e, const TowerW& t, Arena& a, int rows, int B, int T,
   return MMCM_OK;
 }
 
-static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int S, float* pooled, cudaStream_t st) {
+static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int S, float* pooled, cudaStream_t st,
+                    const float* tp = nullptr, const float* ip = nullptr) {
   const mmcm_config& c = e->cfg;
   const TowerW& t = e->text;
   Arena& a = e->at;
@@ -1140,7 +1142,10 @@ static int run_text(Eng* e, const int64_t* ids, const int64_t* mask, int n, int 
   const bool packed = clip && e->opt_varlen_text;   // exact for the causal CLIP tower only (see text_plan_kernel)
   int* const rows_slot = a.rows_dev + (e->stats.text_chunk++ & 255);
   if (packed) {
-    CK(launch_k(text_plan_kernel, dim3(1), dim3(1024), 0, st, ids, n, S, eos, a.seq_start, a.seq_len, a.pool_row, rows_slot));
+    // absent-text shortcut (exact, see text_plan_kernel): only with the presence flags at hand and the option on
+    const int skip_mode = (e->opt_skip_absent && tp && ip) ? (c.head == MMCM_HEAD_FUSION ? 1 : 2) : 0;
+    CK(launch_k(text_plan_kernel, dim3(1), dim3(1024), 0, st, ids, n, S, eos, a.seq_start, a.seq_len, a.pool_row, rows_slot,
+                tp, ip, skip_mode));
     if (t.D == 512)
       CK(launch_k(text_embed_packed_kernel<512>, dim3(blocks), dim3(256), 0, st, ids, mask, e->tok_emb, e->tpos_emb, n, S,
                   c.vocab, a.seq_start, a.seq_len, a.x, e->key_valid));
@@ -1368,7 +1373,7 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
     if (bt < B) {
       const int n = std::min(ct, B - bt);
       CKR(run_text(e, ids + (int64_t)bt * S, mask ? mask + (int64_t)bt * S : nullptr, n, S,
-                   e->pooled_t + (int64_t)bt * c.text_hidden, stx));
+                   e->pooled_t + (int64_t)bt * c.text_hidden, stx, tp + bt, ip + bt));
       bt += n;
     }
     if (bv < B) {
@@ -1904,7 +1909,7 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
     if (bt < B) {
       const int n = std::min(ct, (int)B - bt);
       CKR(run_text(e, e->d_ids + (int64_t)bt * S, dmask ? dmask + (int64_t)bt * S : nullptr, n, S,
-                   e->pooled_t + (int64_t)bt * c.text_hidden, e->s_text));
+                   e->pooled_t + (int64_t)bt * c.text_hidden, e->s_text, e->d_tp + bt, e->d_ip + bt));
       bt += n;
     }
     if (bv < B) {
@@ -2078,6 +2083,7 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   else if (n == "ln_fold") h->opt_ln_fold = value != 0;
   else if (n == "head_cluster") h->opt_head_cluster = value != 0;
   else if (n == "split_k") h->opt_split_k = value != 0;
+  else if (n == "skip_absent_text") h->opt_skip_absent = value != 0;
   else if (n == "narrow_tiles") h->opts.narrow_tiles = value != 0;
   else if (n == "debug_feats") h->opt_debug_feats = value != 0;
   else if (n == "auto_chunk") h->opt_auto_chunk = value != 0;

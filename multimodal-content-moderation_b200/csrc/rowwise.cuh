@@ -269,11 +269,18 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
 //   seq_start[b], seq_len[b]        packed coordinates of sample b
 //   pool_row[b] = seq_start[b] + p_b
 //   rows_total[0] = sum_b L_b        (device-side M of every GEMM / LayerNorm of the chunk)
+// Absent text (skip_mode != 0): a sample whose text feature cannot reach the logits keeps ONE row (its BOS token) --
+//   fusion head (skip_mode 1): text_present < 0.5 zeroes the normalised text feature (R/src/models/fusion.py:188-189)
+//   MTL head    (skip_mode 2): text_present < 0.5 AND image_present >= 0.5 selects the image branch and the gate is
+//                              unused (R/src/models/multitask.py:194-197); with both absent the text branch wins, so
+//                              those samples keep all their rows (measured on the reference)
+// The pooled row of such a sample is a finite value nobody reads through: the logits are bit-identical.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 text_plan_kernel(const int64_t* __restrict__ ids, const int B, const int S, const int eos_id,
                  int* __restrict__ seq_start, int* __restrict__ seq_len, int* __restrict__ pool_row,
-                 int* __restrict__ rows_total) {
+                 int* __restrict__ rows_total, const float* __restrict__ text_present,
+                 const float* __restrict__ image_present, const int skip_mode) {
   __shared__ int warp_tot[32], warp_excl[32];
   __shared__ int carry, slab_total;
   pdl_trigger();
@@ -294,6 +301,7 @@ text_plan_kernel(const int64_t* __restrict__ ids, const int B, const int S, cons
         for (int t = 0; t < S; ++t) if ((int)row[t] == eos_id) { best = t; break; }
       }
       len = best + 1;
+      if (skip_mode && text_present[b] < 0.5f && (skip_mode == 1 || image_present[b] >= 0.5f)) len = 1;
     }
     int incl = len;                 // inclusive scan inside the warp
 #pragma unroll

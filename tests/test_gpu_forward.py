@@ -316,6 +316,34 @@ def test_small_forward_split_k_matches_unsplit(name):
     m.set_option("pooled_last_layer", 1)
 
 
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened"])
+def test_absent_text_shortcut_is_bit_identical(name):
+    """Packed text: a sample whose text feature cannot reach the logits (fusion: text_present = 0; MTL: text absent AND
+    image present -- with both absent the MTL head still reads the text branch) keeps a single row of the
+    text tower.  Logits must not move by a bit, and they must still match the oracle."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    batch = syn.make_inputs(a, 48, seed=1234, edge_rows=True)
+    g = torch.Generator().manual_seed(5)
+    batch["text_present"] = (torch.rand(48, generator=g) > 0.4).float()
+    batch["image_present"] = (torch.rand(48, generator=g) > 0.3).float()
+    batch["text_present"][:4] = torch.tensor([0., 0., 1., 1.])
+    batch["image_present"][:4] = torch.tensor([0., 1., 0., 1.])           # all four combinations are present
+    with torch.no_grad():
+        ref = oracle_forward(kind, a, sd, batch)
+    d = {k: v.to("cuda:0") for k, v in batch.items()}
+    m.set_option("varlen_text", 1)
+    m.set_option("skip_absent_text", 0)
+    y0 = m(**d)["logits"].cpu()
+    m.set_option("skip_absent_text", 1)
+    y1 = m(**d)["logits"].cpu()
+    assert torch.equal(y1, y0)
+    _gate(y1, ref, True, kind, a)
+    m.set_option("varlen_text", 0)                                         # dense text: the shortcut does not apply
+    assert torch.equal(m(**d)["logits"].cpu(), y0)
+
+
 def test_cuda_graph_survives_buffer_growth():
     """A graph captured at B=8 bakes the arena / pooled-buffer pointers.  A later, larger batch reallocates them; the
     next B=8 call must not replay into freed memory: graphs are dropped with the buffers and re-captured."""

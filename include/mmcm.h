@@ -129,7 +129,8 @@ MMCM_API int mmcm_forward_host_u8(mmcm_handle h, const int64_t* input_ids, const
                          void* stream);
 
 /* Introspection ------------------------------------------------------------------------------ */
-/* Copies an intermediate of the LAST forward into dst (device fp32).  Names: "text_pooled",
+/* Copies an intermediate of the LAST forward into dst (device fp32).  (With "skip_absent_text" the text rows of samples
+ * whose text cannot reach the logits hold the BOS row's output, not the reference's pooler output.)  Names: "text_pooled",
  * "vision_pooled" (tower pooler_output, fp32 [B,D]), "text_hidden", "vision_hidden" (residual stream
  * fp32 [B*T,D]: after the last layer with option "pooled_last_layer" = 0; with the default 1 the last layer only
  * advances the pooled rows, so these hold the last layer's INPUT).  *numel_out receives the element count. */

@@ -102,3 +102,20 @@ def test_focal_loss_formula():
         assert torch.allclose(FocalWithLogitsLoss(alpha, 2.0, "mean")(z, t), ref.mean(), atol=1e-6)
         assert torch.allclose(FocalWithLogitsLoss(None, 2.0, "sum")(z, t),
                               (ce * (1 - (p * t + (1 - p) * (1 - t))) ** 2.0).sum(), atol=1e-4)
+
+
+def test_resolve_arch_rejects_unknown_encoders_and_knows_siglip_v1():
+    """an unknown `encoder_name` used to fall through silently to a CLIP / SigLIP2 shape."""
+    import pytest
+    from mmcm_b200 import arch as A
+    assert A.resolve_arch("openai/clip-vit-base-patch32", "clip") is A.CLIP_B32
+    assert A.resolve_arch("/data/ckpt/my-finetune-of-clip-vit-base-patch16", "clip") is A.CLIP_B16
+    assert A.resolve_arch("google/siglip-base-patch16-224", "siglip").vocab == 32000       # SigLIP v1 vocabulary
+    assert A.resolve_arch("google/siglip2-base-patch16-224", "siglip").vocab == 256000
+    with pytest.raises(ValueError, match="unknown encoder_name"):
+        A.resolve_arch("facebook/some-other-model", "clip")
+    with pytest.raises(ValueError, match="architecture but backend"):
+        A.resolve_arch("openai/clip-vit-base-patch32", "siglip")
+    A.register_arch("my/clip-l14", A.CLIP_B16)
+    assert A.resolve_arch("my/clip-l14", "clip") is A.CLIP_B16
+    assert A.IMAGE_NORM[A.BACKEND_SIGLIP] == ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))

@@ -1861,7 +1861,11 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   // the towers of chunk i; the text tower does not wait for pixels at all
   // stage size: ~200 MB of pixels (measured on B=1024: fp32 pixels best at 342 samples per stage, 51.6 k vs 50.3 k at
   // 256; uint8 pixels best unsplit, 53.4 k vs 49.9 k -- tools/e2e_sweep.py); option "host_chunk" overrides
-  const int auto_chunk = std::max<int64_t>(64, ((int64_t)200 << 20) / (int64_t)px_bytes);
+  int auto_chunk = (int)std::max<int64_t>(64, ((int64_t)200 << 20) / (int64_t)px_bytes);
+  // a batch that would be ONE stage gets two (2/3 + 1/3) once it is big enough for the second copy to be worth hiding:
+  // batch 256, fp32 pixels: 43.7 k -> 46.7 k samples/s; below ~192 samples one stage is better (tools/e2e_sweep.py,
+  // profiles/r02_e2e_stage_sweep.txt)
+  if (!hpx.u8 && B >= 192 && B <= auto_chunk) auto_chunk = (2 * B + 2) / 3;
   const int vcap = std::min(e->opt_micro_batch, e->opt_host_chunk > 0 ? e->opt_host_chunk : auto_chunk);
   const int cv = e->opt_auto_chunk ? choose_chunk(e->vis, vis_tokens(c), B, vcap, g_num_sms) : std::min((int)B, vcap);
   e->last_chunk_text = ct; e->last_chunk_vis = cv;

@@ -34,7 +34,8 @@ def call():
                          host["image_present"], out=out)
 
 
-for chunk in (128, 192, 256, 342, 512, 1024):
+chunks = [int(c) for c in sys.argv[3].split(",")] if len(sys.argv) > 3 else [128, 192, 256, 342, 512, 1024]
+for chunk in chunks:
     m.set_option("host_chunk", chunk)
     for _ in range(3):
         call()

@@ -1875,7 +1875,9 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   // copies of the previous call took > 85 % of its time) the step is "all copies, then the towers of the LAST stage":
   // taper the last stages (cv, ..., cv/2, cv/4, cv/4) so that little work is left when the last bytes land.  When the
   // towers are the bottleneck equal stages are better (fewer, fuller GEMM rounds), so the schedule follows what the
-  // previous call measured (8 GPUs, 23 GB/s per rank: 287 k -> see profiles/r02_bench_8gpu*.json).
+  // previous call measured (8 GPUs, 23 GB/s per rank: 287 k -> 295 k samples/s, profiles/r02_bench_8gpu*.json).  A small
+  // FIRST stage, so that the vision tower starts sooner, measured slower on one GPU (55.2 k -> 52.1-53.3 k for 48-171
+  // samples, profiles/r02_e2e_stage_sweep.txt): not done.
   std::vector<int> stages;
   {
     int left = B;

@@ -180,8 +180,11 @@ MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out,
  *                      pairs share the weight stream; 0 = 256-column tiles always.  Same per-element k order: identical bits.
  *   "skip_absent_text" 1 = default (with varlen_text): a sample whose text feature cannot reach the logits -- fusion head:
  *                      text_present < 0.5 (fusion.py:188-189); MTL head: text_present < 0.5 and image_present >= 0.5
- *                      (multitask.py:194-197) -- keeps one row of the packed text tower instead of up to 77;
- *                      bit-identical logits; 0 = every sample runs its text rows
+ *                      (multitask.py:194-197) -- keeps one row of the packed text tower instead of up to 77; and a
+ *                      forward in which NO sample has an image (or usable text) skips that tower altogether (flags are
+ *                      read on the host: directly in mmcm_forward_host*, by one small read-back in mmcm_forward* when
+ *                      B <= 16 and the stream is not being captured).  Bit-identical logits; the "text_pooled" /
+ *                      "vision_pooled" stages of skipped samples hold placeholders.  0 = every sample runs both towers
  *   "split_k"          1 = default: in forwards with B < 16 the residual GEMMs (out_proj, fc2) split their K loop over
  *                      up to 4 CTA pairs per tile; the partial sums are added to the residual stream, in a fixed order,
  *                      by the LayerNorm kernel that follows (deterministic; no reduction launch); 0 = one pair per tile

@@ -1346,12 +1346,42 @@ static int ensure_static_io(Eng* e, int64_t B) {
   return MMCM_OK;
 }
 
+// Whole-tower skip (exact): when NO sample of a forward has an image, the vision tower's output cannot reach
+// a logit (fusion: feature x image_present = 0, fusion.py:188-189; MTL: image_present < 0.5 selects the text branch,
+// multitask.py:194-197), and likewise the text tower when no sample's text can (fusion: text_present < 0.5; MTL: text
+// absent AND image present).  The pooled buffer is zero-filled instead; the logits are bit-identical.  The online
+// callers build such batches all the time (a text-only or image-only request is B = 1, inference.py:201-211).
+// `htp` / `hip`: HOST copies of the presence flags.
+static void towers_needed(const Eng* e, const float* htp, const float* hip, int B, bool* text, bool* vision) {
+  bool t = false, v = false;
+  for (int i = 0; i < B; ++i) {
+    v = v || hip[i] >= 0.5f;
+    t = t || htp[i] >= 0.5f || (e->cfg.head == MMCM_HEAD_MTL && hip[i] < 0.5f);
+  }
+  *text = t;
+  *vision = v;
+}
+constexpr int kFlagPeekBatch = 16;   // device-pointer forwards of at most this many samples read their flags back first
+
 static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const Pixels& px, const float* tp,
                           const float* ip, int B, int S, float* logits, float* probs, cudaStream_t st) {
   const mmcm_config& c = e->cfg;
   e->stats.launches = 0;
   clear_gemm_events(e->stats);
   if (B == 0) return MMCM_OK;
+  bool need_text = true, need_vis = true;
+  if (e->opt_skip_absent && B <= kFlagPeekBatch) {
+    // small forwards are latency bound and skipping a tower halves them; one 2 x B-float read-back (the callers
+    // synchronise for the logits right afterwards anyway).  Not while the stream is being captured into a graph.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      float flags[2 * kFlagPeekBatch];
+      CK(cudaMemcpyAsync(flags, tp, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(flags + kFlagPeekBatch, ip, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      towers_needed(e, flags, flags + kFlagPeekBatch, B, &need_text, &need_vis);
+    }
+  }
   e->fold_forward = e->opt_ln_fold && B >= kLnFoldMinBatch;
   e->split_forward = e->opt_split_k && e->opts.tma_epilogue && B < kLnFoldMinBatch &&
                      (int64_t)B * std::max(e->cfg.max_pos, vis_tokens(e->cfg)) <= kSplitRows;
@@ -1369,7 +1399,9 @@ static int forward_device(Eng* e, const int64_t* ids, const int64_t* mask, const
     CK(cudaStreamWaitEvent(svx, e->ev_fork, 0));
   }
   // enqueue the two towers' chunks alternately so that neither stream starves while the host is still launching
-  for (int bt = 0, bv = 0; bt < B || bv < B;) {
+  if (!need_text) CK(cudaMemsetAsync(e->pooled_t, 0, (size_t)B * c.text_hidden * sizeof(float), stx));
+  if (!need_vis) CK(cudaMemsetAsync(e->pooled_v, 0, (size_t)B * c.vis_hidden * sizeof(float), svx));
+  for (int bt = need_text ? 0 : B, bv = need_vis ? 0 : B; bt < B || bv < B;) {
     if (bt < B) {
       const int n = std::min(ct, B - bt);
       CKR(run_text(e, ids + (int64_t)bt * S, mask ? mask + (int64_t)bt * S : nullptr, n, S,
@@ -1896,10 +1928,12 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev_chunk.push_back(ev);
   }
+  bool need_text = true, need_vis = true;
+  if (e->opt_skip_absent) towers_needed(e, text_present, image_present, B, &need_text, &need_vis);   // host flags: no read-back
   CK(cudaEventRecord(e->ev_fork, st));
   CK(cudaEventRecord(e->ev_t0, st));
   CK(cudaStreamWaitEvent(e->s_copy, e->ev_fork, 0));
-  for (int ci = 0, b0 = 0; ci < nchunks; b0 += stages[ci], ++ci) {
+  for (int ci = 0, b0 = 0; need_vis && ci < nchunks; b0 += stages[ci], ++ci) {   // no images at all: nothing to ship
     const int n = stages[ci];
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(e->d_px) + b0 * px_bytes, hsrc + b0 * px_bytes, (size_t)n * px_bytes,
                        cudaMemcpyHostToDevice, e->s_copy));
@@ -1911,7 +1945,9 @@ static int forward_host_impl(Eng* e, const int64_t* input_ids, const int64_t* at
   CK(cudaStreamWaitEvent(e->s_text, e->ev_fork, 0));
   CK(cudaStreamWaitEvent(e->s_vis, e->ev_fork, 0));
   const int64_t* dmask = attention_mask ? e->d_mask : nullptr;
-  for (int bt = 0, bv = 0, ci = 0; bt < B || bv < B;) {
+  if (!need_text) CK(cudaMemsetAsync(e->pooled_t, 0, (size_t)B * c.text_hidden * sizeof(float), e->s_text));
+  if (!need_vis) CK(cudaMemsetAsync(e->pooled_v, 0, (size_t)B * c.vis_hidden * sizeof(float), e->s_vis));
+  for (int bt = need_text ? 0 : B, bv = need_vis ? 0 : B, ci = 0; bt < B || bv < B;) {
     if (bt < B) {
       const int n = std::min(ct, (int)B - bt);
       CKR(run_text(e, e->d_ids + (int64_t)bt * S, dmask ? dmask + (int64_t)bt * S : nullptr, n, S,

@@ -348,6 +348,41 @@ def test_absent_text_shortcut_is_bit_identical(name):
     assert torch.equal(m(**d)["logits"].cpu(), y0)
 
 
+@pytest.mark.parametrize("name", ["clip_fusion_hardened", "clip_mtl_h256_hardened", "siglip_fusion_hardened"])
+def test_whole_tower_skip_for_single_modality_requests(name):
+    """Text-only / image-only requests (the B = 1 dicts of R/scripts/inference.py:201-211 with one presence flag 0): when
+    no sample of a small forward has an image (or usable text) the whole tower is skipped.  Bit-identical logits, about
+    half the launches; through the host-buffer call the pixels are not even shipped."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case(name)
+    m = _make_module(kind, a, kw, sd)
+    for B in (1, 5):
+        base = syn.make_inputs(a, 8, seed=700 + B)
+        base = {k: v[:B].contiguous() for k, v in base.items()}
+        for tp, ip in ((1.0, 0.0), (0.0, 1.0), (0.0, 0.0)):
+            batch = dict(base)
+            batch["text_present"] = torch.full((B,), tp)
+            batch["image_present"] = torch.full((B,), ip)
+            with torch.no_grad():
+                ref = oracle_forward(kind, a, sd, batch)
+            d = {k: v.to("cuda:0") for k, v in batch.items()}
+            m.set_option("skip_absent_text", 0)
+            y0 = m(**d)["logits"].cpu()
+            n0 = m._engine.last_launch_count()
+            m.set_option("skip_absent_text", 1)
+            y1 = m(**d)["logits"].cpu()
+            n1 = m._engine.last_launch_count()
+            assert torch.equal(y1, y0), f"B={B} text_present={tp} image_present={ip}"
+            assert (y1 - ref).abs().max().item() <= REL_GATE[_gate_key(kind, a)] * 3.3
+            both_absent_mtl = kind == "mtl" and tp == 0.0 and ip == 0.0      # the MTL head then reads the text branch
+            skipped = (ip == 0.0) + (tp == 0.0 and not both_absent_mtl and not (kind == "mtl" and ip == 0.0))
+            assert (n1 < n0 - 50) == (skipped > 0), (n0, n1, tp, ip)
+            pinned = {k: v.pin_memory() for k, v in batch.items()}
+            host = m._engine.forward_host(pinned["input_ids"], pinned["attention_mask"], pinned["pixel_values"],
+                                          pinned["text_present"], pinned["image_present"])
+            assert torch.equal(host, y0)
+
+
 def test_cuda_graph_survives_buffer_growth():
     """A graph captured at B=8 bakes the arena / pooled-buffer pointers.  A later, larger batch reallocates them; the
     next B=8 call must not replay into freed memory: graphs are dropped with the buffers and re-captured."""

@@ -279,7 +279,10 @@ def main():
                          "layers); 0 = separate normalisation pass. The other setting is reported under `extras`")
     ap.add_argument("--pairs-text", type=int, default=0, help="CTA pairs the text-tower GEMMs may occupy (0 = all 74)")
     ap.add_argument("--pairs-vision", type=int, default=0)
-    ap.add_argument("--attention-impl", type=int, default=0, help="0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256")
+    ap.add_argument("--attention-impl", type=int, default=0,
+                    help="0 auto, 1 cp.async mma.sync, 2 tcgen05 wherever T <= 256, 3 TMA-ring mma.sync for 32 < T <= 80")
+    ap.add_argument("--attention-ring", type=int, default=1,
+                    help="0 = auto keeps the 77-token text tower on the cp.async kernel of round 1 (A/B runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -344,6 +347,7 @@ def main():
     m.set_option("pairs_text", args.pairs_text)
     m.set_option("pairs_vision", args.pairs_vision)
     m.set_option("attention_impl", args.attention_impl)
+    m.set_option("attention_ring", args.attention_ring)
     eng = m._ensure_engine(local_rank)
 
     B = args.batch
@@ -418,6 +422,8 @@ def main():
                                             "layer's out_proj, LN2, MLP and final LN: those ops are row-wise, logits are "
                                             f"bit-identical; the headline `value` uses {args.pooled_last}"}
         extras[f"value_ln_fold_{1 - args.ln_fold}"] = timed_variant("ln_fold", 1 - args.ln_fold, args.ln_fold)
+        extras[f"value_attention_ring_{1 - args.attention_ring}"] = timed_variant(
+            "attention_ring", 1 - args.attention_ring, args.attention_ring)
         if a.backend == 0:
             extras[f"value_varlen_text_{1 - args.varlen}"] = timed_variant("varlen_text", 1 - args.varlen, args.varlen)
             extras["note"] = ("varlen_text=1 packs the causal CLIP text tower up to each sample's EOS row (bit-identical "

@@ -154,7 +154,7 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
 MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out, double* flops_out, double* bytes_out,
                                 int64_t* launches_out);
 /* Options (name -> meaning).  Every option is per handle; h == NULL edits the defaults that the stand-alone kernels
- * below use ("pdl", "tma_epilogue", "attention_impl", "narrow_tiles" only):
+ * below use ("pdl", "tma_epilogue", "attention_impl", "attention_ring", "narrow_tiles" only):
  *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)
  *   "micro_batch"      upper bound on the samples per internal pass of a tower (default 1024)
  *   "auto_chunk"       1 = pick, per tower, the chunk <= micro_batch whose GEMM tile counts fill whole rounds of the
@@ -191,7 +191,11 @@ MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out,
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
  *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
- *                      for 128 < T <= 256, mma.sync kernel otherwise; 1 = mma.sync always; 2 = tcgen05 whenever T <= 256
+ *                      for 128 < T <= 256, the TMA-ring mma.sync kernel for 64 < T <= 80 (the 77-token CLIP text tower,
+ *                      dense and packed), the cp.async mma.sync kernel otherwise; 1 = cp.async mma.sync always;
+ *                      2 = tcgen05 whenever T <= 256; 3 = TMA-ring mma.sync wherever it exists (32 < T <= 80)
+ *   "attention_ring"   1 = default; 0 = auto never picks the TMA-ring kernel (round-1 behaviour, for A/B runs).  The ring
+ *                      kernel is bit-identical to the cp.async one (same fragments and order of operations)
  *   "pdl"              1 = every kernel is launched with programmatic stream serialization (prologues overlap the
  *                      previous kernel's tail)
  *   "graph_max_batch"  forwards with B <= this are replayed as one CUDA graph from the third call of a shape on

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_ring.cuh"
 #include "attention_tc.cuh"
 #include "common.cuh"
 #include "gemm2_tcgen05.cuh"
@@ -76,7 +77,8 @@ static int g_num_sms = kNumSMs;
 struct LaunchOpts {
   bool pdl = true;            // programmatic dependent launch on every kernel
   bool tma_epilogue = true;   // TMA tile-store / reduce-add epilogue of the pair GEMM
-  int attention_impl = 0;     // 0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256
+  int attention_impl = 0;     // 0 auto, 1 mma.sync, 2 tcgen05 wherever T <= 256, 3 TMA-ring mma.sync for 32 < T <= 80
+  int attention_ring = 1;     // auto: 77-token text on the TMA-ring kernel (0 = the cp.async kernel of round 1)
   int pair_limit = 0;         // > 0: cap the CTA pairs a GEMM launch may occupy (SM partitioning between the towers)
   bool narrow_tiles = true;   // GEMMs with one row block (M <= 256) use 64 / 128-column tiles
 };
@@ -424,6 +426,30 @@ static int launch_att(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, 
   return MMCM_OK;
 }
 
+// TMA-ring variant of the mma.sync kernel (attention_ring.cuh): one persistent CTA per SM
+template <int TPAD, int NG, int NSTAGES>
+static int launch_att_ring(const bf16* qkv, bf16* out, const uint8_t* kvalid, int B, int T, int heads, int causal,
+                           cudaStream_t st, const int* seq_start, const int* seq_len) {
+  using C = AttRingCfg<TPAD, NG, NSTAGES>;
+  CKR(ensure_driver());
+  auto kern = attention_ring_kernel<TPAD, NG, NSTAGES>;
+  static AttrOnce once;
+  if (once.need()) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  const int D = heads * ATT_DH;
+  AttRingMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int k = 0; k < C::QW; ++k) CKR(get_tmap(&maps.m[k], qkv, (int64_t)B * T, 3 * D, 16 * (k + 1), false));
+  const int total = B * heads;
+  int grid = g_num_sms;
+  if (grid > total) grid = total;
+  CK(launch_k(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, maps, out, kvalid, seq_start, seq_len, T, D, causal, T, B,
+              heads));
+  return MMCM_OK;
+}
+
 static long long* g_gemm_trace = nullptr;   // dev tool, see mmcm_debug_set_gemm_trace
 // 0 = auto: tcgen05 kernel when at least two samples share a 128-row tile (T <= 64: measured 80 vs 87 us for the
 // 50-token vision tower) and for 128 < T <= 256 (SigLIP vision), mma.sync kernel otherwise (77-token text: 90 vs
@@ -471,6 +497,16 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
   if (B <= 0) return MMCM_OK;
   const bool tc128 = T <= 128 && (t_opts->attention_impl == 2 || (t_opts->attention_impl == 0 && T <= 64 && !seq_start));
   const bool tc256 = T > 128 && T <= 256 && !seq_start && t_opts->attention_impl != 1;
+  // 3 = TMA-ring mma.sync kernel wherever it is instantiated (32 < T <= 80); auto picks it for the 77-token text tower,
+  // dense and packed alike (so the two stay bit-identical)
+  const int ring = (t_opts->attention_impl == 3 && T > 32 && T <= 80) ? (T <= 64 ? 64 : 80)
+                   : (t_opts->attention_impl == 0 && T > 64 && T <= 80 && t_opts->attention_ring) ? 80 : 0;
+  if (ring) {
+    if (ring == 64) CKR((launch_att_ring<64, 5, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
+    else CKR((launch_att_ring<80, 4, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
+    if (stats) stats->launches++;
+    return MMCM_OK;
+  }
   if (tc128 || tc256) {
     if (tc128) CKR(launch_attention_tc<128>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
     else CKR(launch_attention_tc<256>(qkv, kvalid, B, T, heads, causal, out, st, seq_start, seq_len));
@@ -2099,7 +2135,8 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
     const std::string d(name);
     if (d == "pdl") g_default_opts.pdl = value != 0;
     else if (d == "tma_epilogue") g_default_opts.tma_epilogue = value != 0;
-    else if (d == "attention_impl" && value >= 0 && value <= 2) g_default_opts.attention_impl = (int)value;
+    else if (d == "attention_impl" && value >= 0 && value <= 3) g_default_opts.attention_impl = (int)value;
+    else if (d == "attention_ring") g_default_opts.attention_ring = value != 0;
     else if (d == "narrow_tiles") g_default_opts.narrow_tiles = value != 0;
     else return fail(MMCM_EINVAL, "option '%s' = %lld cannot be set without a handle", name, (long long)value);
     return MMCM_OK;
@@ -2119,9 +2156,10 @@ int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {
   } else if (n == "pdl") h->opts.pdl = value != 0;
   else if (n == "tma_epilogue") h->opts.tma_epilogue = value != 0;
   else if (n == "attention_impl") {
-    if (value < 0 || value > 2) return fail(MMCM_EINVAL, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05 for T <= 128)");
+    if (value < 0 || value > 3)
+      return fail(MMCM_EINVAL, "attention_impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05 for T <= 256) or 3 (TMA-ring mma.sync)");
     h->opts.attention_impl = (int)value;
-  }
+  } else if (n == "attention_ring") h->opts.attention_ring = value != 0;
   else if (n == "ln_fold") h->opt_ln_fold = value != 0;
   else if (n == "head_cluster") h->opt_head_cluster = value != 0;
   else if (n == "split_k") h->opt_split_k = value != 0;

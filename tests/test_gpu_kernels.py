@@ -318,3 +318,64 @@ def test_attention(lib, T, H, causal, masked, impl):
     if masked:
         assert (out.view(B, T, D)[0] == 0).all()
     _check(lib.mmcm_set_option(None, b"attention_impl", 0))
+
+
+def _attention_inputs(B, T, H, masked, seed):
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g)
+    qkv[:, :D] *= 0.25
+    qkv = qkv.bfloat16()
+    kvalid = None
+    if masked:
+        lens = torch.randint(1, T + 1, (B,), device="cuda", generator=g)
+        kvalid = (torch.arange(T, device="cuda")[None] < lens[:, None]).to(torch.uint8)
+        kvalid[0] = 0
+        kvalid[1, ::3] = 0           # holes, not only a padded tail
+        kvalid = kvalid.contiguous()
+    return qkv, kvalid
+
+
+def _run_attention(lib, impl, qkv, kvalid, B, T, H, causal):
+    _check(lib.mmcm_set_option(None, b"attention_impl", impl))
+    out = torch.full((B * T, H * 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    try:
+        _check(lib.mmcm_attention(qkv.data_ptr(), None if kvalid is None else kvalid.data_ptr(), B, T, H, causal,
+                                  out.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+    finally:
+        _check(lib.mmcm_set_option(None, b"attention_impl", 0))
+    return out
+
+
+@pytest.mark.parametrize("T,H,causal,masked", [
+    (77, 8, 1, True), (77, 8, 1, False), (77, 8, 0, True), (50, 12, 0, False), (64, 12, 0, True), (40, 8, 1, True),
+    (80, 8, 0, True), (33, 8, 1, False), (48, 12, 1, True)])
+def test_attention_ring_is_bit_identical_to_the_cp_async_kernel(lib, T, H, causal, masked):
+    """attention_ring.cuh keeps the fragments and the order of operations of attention.cuh and only skips key tiles
+    whose probabilities are exact zeros: same bits.  B * H > 148 SMs x 8 stages, so every stage of the ring is reused
+    and the mbarrier phases wrap."""
+    B = 170
+    qkv, kvalid = _attention_inputs(B, T, H, masked, T * 7 + H + causal)
+    a = _run_attention(lib, 1, qkv, kvalid, B, T, H, causal)
+    b = _run_attention(lib, 3, qkv, kvalid, B, T, H, causal)
+    assert torch.equal(a, b)
+    ref = _ref_attention(qkv[: 6 * T], 6, T, H, causal, None if kvalid is None else kvalid[:6])
+    assert (b[: 6 * T].float() - ref).abs().max().item() < 3e-2
+    if masked:
+        assert (b.view(B, T, H * 64)[0] == 0).all()
+
+
+@pytest.mark.parametrize("T,causal", [(77, 1), (77, 0), (50, 0)])
+def test_attention_ring_isolates_non_finite_neighbours(lib, T, causal):
+    """The TMA box of a sample covers 16 * ceil(T / 16) rows: the rows behind the sequence belong to the NEXT sample.
+    A corrupt neighbour (NaN / inf in its q, k, v) must not reach this sample through 0 * NaN."""
+    B, H = 40, 8
+    qkv, _ = _attention_inputs(B, T, H, False, 99 + T)
+    clean = _run_attention(lib, 3, qkv, None, B, T, H, causal)
+    bad = qkv.clone().view(B, T, -1)
+    bad[1::2] = float("nan")
+    bad[3, 0] = float("inf")
+    got = _run_attention(lib, 3, bad.view(B * T, -1).contiguous(), None, B, T, H, causal).view(B, T, -1)
+    assert torch.equal(got[0::2], clean.view(B, T, -1)[0::2])
+    assert torch.isfinite(got[0::2].float()).all()

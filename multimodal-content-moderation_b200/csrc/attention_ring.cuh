@@ -13,12 +13,15 @@
 //                the metadata of the following items is loaded two and three iterations ahead
 //   NG groups    of QW = TPAD/16 consumer warps; group g takes every NG-th item of the CTA.  Warp w of a group owns
 //                query rows 16w .. 16w+15 exactly as in attention.cuh (same fragments, same order of operations: the
-//                results are bit-identical to attention_kernel), but key tiles that the causal mask or the sequence
+//                results are bit-identical to attention_kernel), but 16-key steps that the causal mask or the sequence
 //                length hides from ALL 16 rows are skipped (their probabilities are exact zeros), the normalised O
 //                tile is transposed through the warp's own (dead) Q rows and stored as 128-byte lines, and no block
 //                barrier exists: a stage is handed over through one full / one empty mbarrier.
 //
-// One persistent CTA per SM (7 x 30 KB stages for the text tower): four items in flight while four are computed.
+// One persistent CTA per SM (7 x 30 KB stages for the text tower): three items in flight while four are computed.
+// Measured (ncu, 1024 x 77 x 8 heads, profiles/r02_attention_ring_ncu.txt): 96.7 -> 72 us, 4.2 TB/s of DRAM traffic.
+// Tried and dropped: a contiguous run of items per CTA instead of round-robin (same 80 us at that stage: DRAM page
+// locality is not the limit), mbarrier.try_wait with a suspend-time hint (same duration, same instruction count).
 // Rows of the box beyond the sequence (T .. 16*ceil(T/16)-1) belong to the next sample or to stale arena memory; their
 // keys are masked by a select, their V rows are zeroed in shared memory before P V so that a non-finite neighbour can
 // never leak into this sample (0 * NaN) -- the semantics stay those of attention.cuh / SDPA safe softmax.
@@ -55,6 +58,147 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// One warp, one item: query rows r0 .. r0+15 against the first `kmax` key steps (16 keys = two 8-key tiles each) of the
+// staged K / V tiles.  Fragments and order of operations are those of attention_kernel (attention.cuh).  A skipped
+// step is one warp-uniform branch around two interleaved accumulator chains.  (One straight-line instantiation per
+// step count -- a switch over kmax -- was tried: 3.8 k SASS instructions, 80 -> 130 us: the five warps of a group sit
+// in five different bodies and the instruction cache thrashes.)
+template <int KM>
+__device__ __forceinline__ void atr_item(const uint32_t Qs, const uint32_t Ks, const uint32_t Vs,
+                                         const uint32_t (&vmask)[4], const int T, const int r0, const int causal,
+                                         const int lane, __nv_bfloat16* __restrict__ orow, const int D, const int kmax) {
+  constexpr int NTK = 2 * KM;
+  const int g = lane >> 2, tq = lane & 3;
+  const int m = lane >> 3, rr = lane & 7;
+
+  // ---- S = Q K^T
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int qrow = r0 + rr + ((m & 1) << 3);
+    const int chunk = kk * 2 + (m >> 1);
+    ldmatrix_x4(qa[kk], Qs + qrow * 128 + ((chunk ^ rr) << 4));
+  }
+  float s[NTK][4];
+#pragma unroll
+  for (int kk = 0; kk < KM; ++kk) {
+    const int j0 = 2 * kk, j1 = 2 * kk + 1;
+    s[j0][0] = s[j0][1] = s[j0][2] = s[j0][3] = 0.f;
+    s[j1][0] = s[j1][1] = s[j1][2] = s[j1][3] = 0.f;
+    if (kk < kmax) {
+      uint32_t ka0[4], ka1[4], kb0[4], kb1[4];
+      ldmatrix_x4(ka0, Ks + (j0 * 8 + rr) * 128 + ((m ^ rr) << 4));          // tile j0, dh 0..31
+      ldmatrix_x4(ka1, Ks + (j0 * 8 + rr) * 128 + (((4 + m) ^ rr) << 4));    //          dh 32..63
+      ldmatrix_x4(kb0, Ks + (j1 * 8 + rr) * 128 + ((m ^ rr) << 4));          // tile j1
+      ldmatrix_x4(kb1, Ks + (j1 * 8 + rr) * 128 + (((4 + m) ^ rr) << 4));
+      mma_bf16_16816(s[j0], qa[0], ka0[0], ka0[1]);
+      mma_bf16_16816(s[j1], qa[0], kb0[0], kb0[1]);
+      mma_bf16_16816(s[j0], qa[1], ka0[2], ka0[3]);
+      mma_bf16_16816(s[j1], qa[1], kb0[2], kb0[3]);
+      mma_bf16_16816(s[j0], qa[2], ka1[0], ka1[1]);
+      mma_bf16_16816(s[j1], qa[2], kb1[0], kb1[1]);
+      mma_bf16_16816(s[j0], qa[3], ka1[2], ka1[3]);
+      mma_bf16_16816(s[j1], qa[3], kb1[2], kb1[3]);
+    }
+  }
+
+  // ---- mask + fp32 softmax (as attention.cuh)
+  const int qr0 = r0 + g, qr1 = r0 + g + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NTK; ++j) {
+    if (j >= 2 * kmax) continue;      // warp-uniform
+    const uint32_t tile_bits = (vmask[(j * 8) / 32] >> ((j * 8) & 31)) & 0xffu;
+    const bool full = tile_bits == 0xffu && (!causal || j * 8 + 7 <= r0);
+    if (full) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = j * 8 + 2 * tq + e;
+        const bool kok = (tile_bits >> (2 * tq + e)) & 1u;
+        const bool ok0 = kok && (!causal || key <= qr0);
+        const bool ok1 = kok && (!causal || key <= qr1);
+        s[j][e] = ok0 ? s[j][e] : -INFINITY;
+        s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
+        mx0 = fmaxf(mx0, s[j][e]);
+        mx1 = fmaxf(mx1, s[j][2 + e]);
+      }
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  if (mx0 == -INFINITY) mx0 = 0.f;  // fully masked row: exp(-inf) = 0 everywhere, sum = 0 -> output 0
+  if (mx1 == -INFINITY) mx1 = 0.f;
+  const float L2E = 1.4426950408889634f;
+  const float nm0 = -mx0 * L2E, nm1 = -mx1 * L2E;
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t p[NTK][2];           // probabilities as bf16 pairs (the A fragments of P V): half the registers of s[][]
+#pragma unroll
+  for (int kk = 0; kk < KM; ++kk) {
+    p[2 * kk][0] = p[2 * kk][1] = p[2 * kk + 1][0] = p[2 * kk + 1][1] = 0u;
+    if (kk < kmax) {
+#pragma unroll
+      for (int j = 2 * kk; j < 2 * kk + 2; ++j) {
+        const float e0 = ex2_fast(fmaf(s[j][0], L2E, nm0));
+        const float e1 = ex2_fast(fmaf(s[j][1], L2E, nm0));
+        const float e2 = ex2_fast(fmaf(s[j][2], L2E, nm1));
+        const float e3 = ex2_fast(fmaf(s[j][3], L2E, nm1));
+        sum0 += e0 + e1;
+        sum1 += e2 + e3;
+        p[j][0] = pack_bf16x2(e0, e1);
+        p[j][1] = pack_bf16x2(e2, e3);
+      }
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f;
+  const float inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+
+  // ---- O = P V
+  float o[8][4];
+#pragma unroll
+  for (int jd = 0; jd < 8; ++jd) o[jd][0] = o[jd][1] = o[jd][2] = o[jd][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < KM; ++kk) {
+    if (kk >= kmax) continue;         // warp-uniform
+    uint32_t pa[4];
+    pa[0] = p[2 * kk][0];
+    pa[1] = p[2 * kk][1];
+    pa[2] = p[2 * kk + 1][0];
+    pa[3] = p[2 * kk + 1][1];
+    const int vrow = kk * 16 + rr + ((m & 1) << 3);
+#pragma unroll
+    for (int jd = 0; jd < 8; jd += 2) {
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, Vs + vrow * 128 + (((jd + (m >> 1)) ^ rr) << 4));
+      mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
+      mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
+    }
+  }
+
+  // ---- normalise, transpose through this warp's own (dead) Q rows, store 128-byte lines
+#pragma unroll
+  for (int jd = 0; jd < 8; ++jd) {
+    const uint32_t a = Qs + (r0 + g) * 128 + ((jd ^ g) << 4) + tq * 4;
+    sts32(a, pack_bf16x2(o[jd][0] * inv0, o[jd][1] * inv0));
+    sts32(a + 8 * 128, pack_bf16x2(o[jd][2] * inv1, o[jd][3] * inv1));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + m + 4 * i;
+    const uint4 v = lds128(Qs + row * 128 + ((rr ^ (row & 7)) << 4));
+    if (row < T) stg128(orow + (size_t)row * D + rr * 8, v);
+  }
+}
+
 template <int TPAD, int NG, int NSTAGES>
 __global__ void __launch_bounds__(AttRingCfg<TPAD, NG, NSTAGES>::THREADS, 1)
 attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* __restrict__ out,
@@ -63,7 +207,6 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
                       const int kv_stride, const int B, const int heads) {
   using C = AttRingCfg<TPAD, NG, NSTAGES>;
   constexpr int QW = C::QW;
-  constexpr int NT = TPAD / 8;
   constexpr int KT = TPAD / 16;
   constexpr int VW = (TPAD + 31) / 32;
   extern __shared__ __align__(16) uint8_t atr_smem_raw[];
@@ -158,8 +301,6 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
   // ======================================= consumers =======================================
   const int grp = warp / QW, wq = warp - grp * QW;
   const int r0 = wq * 16;
-  const int g = lane >> 2, tq = lane & 3;
-  const int m = lane >> 3, rr = lane & 7;
   int n = grp;
   for (int item = blockIdx.x + grp * gridDim.x; item < total; item += NG * gridDim.x, n += NG) {
     const int stage = n % NSTAGES;
@@ -170,9 +311,9 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
     const uint32_t Ks = Qs + C::TILE_BYTES;
     const uint32_t Vs = Ks + C::TILE_BYTES;
     const int nb = (T + 15) >> 4;
-    uint32_t vmask[VW];
+    uint32_t vmask[4];
 #pragma unroll
-    for (int w = 0; w < VW; ++w) vmask[w] = (uint32_t)hdr[w];
+    for (int w = 0; w < 4; ++w) vmask[w] = w < VW ? (uint32_t)hdr[w] : 0u;
 
     // V rows of the box behind the sequence: zero them before anybody multiplies them by a zero probability
     if ((T & 15) != 0) {
@@ -189,129 +330,11 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
     }
 
     if (r0 < T) {
-      // key tiles / steps any of this warp's rows can see
-      int jmax = (T + 7) >> 3;
-      if (causal) jmax = min(jmax, 2 * (wq + 1));
-      const int kmax = (jmax + 1) >> 1;
-
-      // ---- S = Q K^T
-      uint32_t qa[4][4];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int qrow = r0 + rr + ((m & 1) << 3);
-        const int chunk = kk * 2 + (m >> 1);
-        ldmatrix_x4(qa[kk], Qs + qrow * 128 + ((chunk ^ rr) << 4));
-      }
-      float s[NT][4];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        if (j < jmax) {
-          const int krow = j * 8 + rr;
-          uint32_t kb0[4], kb1[4];
-          ldmatrix_x4(kb0, Ks + krow * 128 + ((m ^ rr) << 4));          // dh 0..31
-          ldmatrix_x4(kb1, Ks + krow * 128 + (((4 + m) ^ rr) << 4));    // dh 32..63
-          mma_bf16_16816(s[j], qa[0], kb0[0], kb0[1]);
-          mma_bf16_16816(s[j], qa[1], kb0[2], kb0[3]);
-          mma_bf16_16816(s[j], qa[2], kb1[0], kb1[1]);
-          mma_bf16_16816(s[j], qa[3], kb1[2], kb1[3]);
-        }
-      }
-
-      // ---- mask + fp32 softmax (as attention.cuh)
-      const int qr0 = r0 + g, qr1 = r0 + g + 8;
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        if (j < jmax) {
-          const uint32_t tile_bits = (vmask[(j * 8) / 32] >> ((j * 8) & 31)) & 0xffu;
-          const bool full = tile_bits == 0xffu && (!causal || j * 8 + 7 <= r0);
-          if (full) {
-            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int key = j * 8 + 2 * tq + e;
-              const bool kok = (tile_bits >> (2 * tq + e)) & 1u;
-              const bool ok0 = kok && (!causal || key <= qr0);
-              const bool ok1 = kok && (!causal || key <= qr1);
-              s[j][e] = ok0 ? s[j][e] : -INFINITY;
-              s[j][2 + e] = ok1 ? s[j][2 + e] : -INFINITY;
-              mx0 = fmaxf(mx0, s[j][e]);
-              mx1 = fmaxf(mx1, s[j][2 + e]);
-            }
-          }
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      if (mx0 == -INFINITY) mx0 = 0.f;
-      if (mx1 == -INFINITY) mx1 = 0.f;
-      const float L2E = 1.4426950408889634f;
-      const float nm0 = -mx0 * L2E, nm1 = -mx1 * L2E;
-      float sum0 = 0.f, sum1 = 0.f;
-      uint32_t p[NT][2];           // probabilities as bf16 pairs (the A fragments of P V): half the registers of s[][]
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        p[j][0] = p[j][1] = 0u;
-        if (j < jmax) {
-          const float e0 = ex2_fast(fmaf(s[j][0], L2E, nm0));
-          const float e1 = ex2_fast(fmaf(s[j][1], L2E, nm0));
-          const float e2 = ex2_fast(fmaf(s[j][2], L2E, nm1));
-          const float e3 = ex2_fast(fmaf(s[j][3], L2E, nm1));
-          sum0 += e0 + e1;
-          sum1 += e2 + e3;
-          p[j][0] = pack_bf16x2(e0, e1);
-          p[j][1] = pack_bf16x2(e2, e3);
-        }
-      }
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-      const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f;
-      const float inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-
-      // ---- O = P V
-      float o[8][4];
-#pragma unroll
-      for (int jd = 0; jd < 8; ++jd) o[jd][0] = o[jd][1] = o[jd][2] = o[jd][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < KT; ++kk) {
-        if (kk < kmax) {
-          uint32_t pa[4];
-          pa[0] = p[2 * kk][0];
-          pa[1] = p[2 * kk][1];
-          pa[2] = p[2 * kk + 1][0];
-          pa[3] = p[2 * kk + 1][1];
-          const int vrow = kk * 16 + rr + ((m & 1) << 3);
-#pragma unroll
-          for (int jd = 0; jd < 8; jd += 2) {
-            uint32_t vb[4];
-            ldmatrix_x4_trans(vb, Vs + vrow * 128 + (((jd + (m >> 1)) ^ rr) << 4));
-            mma_bf16_16816(o[jd], pa, vb[0], vb[1]);
-            mma_bf16_16816(o[jd + 1], pa, vb[2], vb[3]);
-          }
-        }
-      }
-
-      // ---- normalise, transpose through this warp's own Q rows, store 128-byte lines
-#pragma unroll
-      for (int jd = 0; jd < 8; ++jd) {
-        const uint32_t a = Qs + (r0 + g) * 128 + ((jd ^ g) << 4) + tq * 4;
-        sts32(a, pack_bf16x2(o[jd][0] * inv0, o[jd][1] * inv0));
-        sts32(a + 8 * 128, pack_bf16x2(o[jd][2] * inv1, o[jd][3] * inv1));
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = r0 + m + 4 * i;
-        const uint4 v = lds128(Qs + row * 128 + ((rr ^ (row & 7)) << 4));
-        if (row < T) stg128(out + (size_t)(row0 + row) * D + h * ATT_DH + rr * 8, v);
-      }
+      // key steps (16 keys) any of this warp's rows can see
+      int kmax = nb;
+      if (causal) kmax = min(kmax, wq + 1);
+      __nv_bfloat16* orow = out + (size_t)row0 * D + h * ATT_DH;
+      atr_item<KT>(Qs, Ks, Vs, vmask, T, r0, causal, lane, orow, D, kmax);
     }
     fence_proxy_async();          // generic-proxy writes (O tile, V padding) before the next TMA box lands here
     __syncwarp();

@@ -19,7 +19,8 @@
 //                barrier exists: a stage is handed over through one full / one empty mbarrier.
 //
 // One persistent CTA per SM (7 x 30 KB stages for the text tower): three items in flight while four are computed.
-// Measured (ncu, 1024 x 77 x 8 heads, profiles/r02_attention_ring_ncu.txt): 96.7 -> 72 us, 4.2 TB/s of DRAM traffic.
+// Measured (ncu, 1024 x 77 x 8 heads, profiles/r02_attention_ring_ncu.txt): 96.7 -> 66.4 us = 4.6 TB/s of DRAM
+// traffic (80 us first version, 72 with interleaved chains, 66 with the rotating row blocks).
 // Tried and dropped: a contiguous run of items per CTA instead of round-robin (same 80 us at that stage: DRAM page
 // locality is not the limit), mbarrier.try_wait with a suspend-time hint (same duration, same instruction count).
 // Rows of the box beyond the sequence (T .. 16*ceil(T/16)-1) belong to the next sample or to stale arena memory; their
@@ -299,10 +300,16 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
   }
 
   // ======================================= consumers =======================================
-  const int grp = warp / QW, wq = warp - grp * QW;
-  const int r0 = wq * 16;
+  const int grp = warp / QW, wlocal = warp - grp * QW;
   int n = grp;
+  int rot = 0;                   // rounds of this group, modulo QW
   for (int item = blockIdx.x + grp * gridDim.x; item < total; item += NG * gridDim.x, n += NG) {
+    // Causal: row block w costs w + 1 key steps, so the block a warp owns rotates from item to item -- every warp
+    // sees the same work over QW items, and since the warps of a group only meet at the stage's empty barrier the
+    // warp that drew a light block already works on the group's next item while the heavy block finishes.
+    const int wq = causal ? (wlocal + rot >= QW ? wlocal + rot - QW : wlocal + rot) : wlocal;
+    rot = rot + 1 == QW ? 0 : rot + 1;
+    const int r0 = wq * 16;
     const int stage = n % NSTAGES;
     mbar_wait(bars + 16 * stage, (uint32_t)(n / NSTAGES) & 1u);
     const int* hdr = hdr_all + stage * C::HDR_WORDS;

@@ -157,7 +157,7 @@ def gemm_traffic(model):
         return None, "no ncu capture of this model in profiles/r02_gemm_traffic.json"
 
 
-def _by_epilogue(eng, peaks):
+def _by_epilogue(eng, peaks, a=None):
     """The GEMM launches of the last timed forward, split by epilogue kind.  The residual GEMMs (out_proj, fc2:
     EPI_RESID_STATS) carry the fp32 residual-stream read-modify-write and the bf16 copy -- the LayerNorm pass of round 1
     lives in them -- so they are reported against BOTH rooflines; the others against the tensor pipe."""
@@ -165,12 +165,30 @@ def _by_epilogue(eng, peaks):
              4: "resid_stats (out_proj, fc2 + LayerNorm statistics + bf16 copy)", 5: "lnfold_bf16 (LayerNorm + qkv)",
              6: "lnfold_act_bf16 (LayerNorm + fc1 + activation)"}
     out = {}
+
+    def entry(ms, fl, by, n):
+        return {"launches": n, "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "frac_tensor": fl / (ms * 1e-3) / 1e12 / peaks["tflops"],
+                "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_hbm": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     for epi, nm in names.items():
         ms, fl, by, n = eng.gemm_time(epi)
         if n == 0 or ms <= 0:
             continue
-        out[nm] = {"launches": n, "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "frac_tensor": fl / (ms * 1e-3) / 1e12 / peaks["tflops"],
-                   "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_hbm": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        out[nm] = entry(ms, fl, by, n)
+    if a is not None:
+        # EPI_RESID_STATS covers two different machines: out_proj (K = D: 85 / 127 FLOP per byte of its own traffic, below
+        # the 209 FLOP/B balance point -> HBM roofline) and fc2 (K = 4 D -> tensor roofline).  Report them apart, each
+        # with the fraction of the roofline that binds it.
+        split = {}
+        for tower, t in (("text", a.text), ("vision", a.vision)):
+            for nm, (N, K) in (("out_proj", (t.hidden, t.hidden)), ("fc2", (t.hidden, t.ffn))):
+                ms, fl, by, n = eng.gemm_time(4, N=N, K=K)
+                if n and ms > 0:
+                    e = entry(ms, fl, by, n)
+                    e["bound"] = "hbm" if nm == "out_proj" else "tensor"
+                    e["frac_of_bound"] = e["frac_hbm"] if nm == "out_proj" else e["frac_tensor"]
+                    split[f"{tower}.{nm} (N={N}, K={K})"] = e
+        if split:
+            out["resid_stats_by_shape"] = split
     return out
 
 
@@ -555,7 +573,7 @@ def main():
         for _ in range(3):                  # median of three passes: a single 19 ms forward is sensitive to clock dips
             m(**batch)
             torch.cuda.synchronize()
-            passes.append(eng.gemm_time() + (_by_epilogue(eng, peaks),))
+            passes.append(eng.gemm_time() + (_by_epilogue(eng, peaks, a),))
         gms, gfl, gn, by_epi = sorted(passes, key=lambda t: t[0])[1]
         m.set_option("time_gemms", 0)
         m.set_option("streams", args.streams)

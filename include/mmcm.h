@@ -153,6 +153,10 @@ MMCM_API int mmcm_gemm_time(mmcm_handle h, double* ms_out, double* flops_out, in
  * fp32 residual stream in HBM, the others by the tensor pipe -- bench.py reports them apart. */
 MMCM_API int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out, double* flops_out, double* bytes_out,
                                 int64_t* launches_out);
+/* The same again, restricted to one weight shape as well (N, K; 0 = any; epilogue -1 = any): out_proj (K = N, bound by
+ * the residual stream in HBM) and fc2 (K = 4 N, bound by the tensor pipe) share EPI_RESID_STATS and are reported apart. */
+MMCM_API int mmcm_gemm_time_shape(mmcm_handle h, int32_t epilogue, int32_t N, int32_t K, double* ms_out,
+                                  double* flops_out, double* bytes_out, int64_t* launches_out);
 /* Options (name -> meaning).  Every option is per handle; h == NULL edits the defaults that the stand-alone kernels
  * below use ("pdl", "tma_epilogue", "attention_impl", "attention_ring", "narrow_tiles" only):
  *   "streams"          1 or 2: text / vision towers on separate internal streams (default 2)

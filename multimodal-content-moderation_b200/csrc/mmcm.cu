@@ -2091,7 +2091,7 @@ static double gemm_algorithmic_bytes(int epi, double m, int N, int K) {
 }
 
 static int gemm_time_impl(mmcm_handle h, int epi, double* ms_out, double* flops_out, int64_t* launches_out,
-                          double* bytes_out = nullptr) {
+                          double* bytes_out = nullptr, int N = 0, int K = 0) {
   if (!h) return fail(MMCM_EINVAL, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
@@ -2099,6 +2099,7 @@ static int gemm_time_impl(mmcm_handle h, int epi, double* ms_out, double* flops_
   int64_t n = 0;
   for (auto& p : h->stats.gemm_events) {
     if (epi >= 0 && p.epi != epi) continue;
+    if ((N > 0 && p.N != N) || (K > 0 && p.K != K)) continue;
     float t = 0;
     CK(cudaEventElapsedTime(&t, p.e0, p.e1));
     ms += t;
@@ -2126,6 +2127,12 @@ int mmcm_gemm_time_epi(mmcm_handle h, int32_t epilogue, double* ms_out, double* 
                        int64_t* launches_out) {
   if (epilogue < 0 || epilogue > EPI_LNFOLD_ACT_BF16) return fail(MMCM_EINVAL, "unknown epilogue %d", epilogue);
   return gemm_time_impl(h, epilogue, ms_out, flops_out, launches_out, bytes_out);
+}
+
+int mmcm_gemm_time_shape(mmcm_handle h, int32_t epilogue, int32_t N, int32_t K, double* ms_out, double* flops_out,
+                         double* bytes_out, int64_t* launches_out) {
+  if (epilogue < -1 || epilogue > EPI_LNFOLD_ACT_BF16) return fail(MMCM_EINVAL, "unknown epilogue %d", epilogue);
+  return gemm_time_impl(h, epilogue, ms_out, flops_out, launches_out, bytes_out, N, K);
 }
 
 int mmcm_set_option(mmcm_handle h, const char* name, int64_t value) {

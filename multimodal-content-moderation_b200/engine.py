@@ -244,10 +244,15 @@ class Engine:
         L.check(self.lib.mmcm_last_chunks(self._h, C.byref(t), C.byref(v)))
         return t.value, v.value
 
-    def gemm_time(self, epilogue: Optional[int] = None):
+    def gemm_time(self, epilogue: Optional[int] = None, N: int = 0, K: int = 0):
         """(ms, executed FLOPs, launches) of the GEMM launches of the last forward run with option time_gemms = 1;
-        `epilogue` restricts the sum to one MMCM_EPI_* kind."""
+        `epilogue` restricts the sum to one MMCM_EPI_* kind (then algorithmic bytes are returned too), `N` / `K` to
+        one weight shape."""
         ms, fl, by, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+        if N or K:
+            L.check(self.lib.mmcm_gemm_time_shape(self._h, -1 if epilogue is None else int(epilogue), int(N), int(K),
+                                                  C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)))
+            return ms.value, fl.value, by.value, n.value
         if epilogue is None:
             L.check(self.lib.mmcm_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
             return ms.value, fl.value, n.value

@@ -52,6 +52,8 @@ _SIGS = {
     "mmcm_gemm_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mmcm_gemm_time_epi": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_int64)]),
+    "mmcm_gemm_time_shape": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mmcm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "mmcm_last_error": (C.c_char_p, []),
     "mmcm_version": (C.c_char_p, []),

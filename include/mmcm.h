@@ -194,12 +194,13 @@ MMCM_API int mmcm_gemm_time_shape(mmcm_handle h, int32_t epilogue, int32_t N, in
  *                      by the LayerNorm kernel that follows (deterministic; no reduction launch); 0 = one pair per tile
  *   "gemm_impl"        0 = tcgen05 CTA-pair kernel, 1 = SIMT validation kernel, 2 = tcgen05 single-CTA kernel
  *   "tma_epilogue"     1 = TMA tile-store / reduce-add epilogue of the pair GEMM, 0 = per-thread stores
- *   "attention_impl"   0 = auto: tcgen05 attention kernel when two or more samples share a 128-row tile (T <= 64) and
- *                      for 128 < T <= 256, the TMA-ring mma.sync kernel for 64 < T <= 80 (the 77-token CLIP text tower,
- *                      dense and packed), the cp.async mma.sync kernel otherwise; 1 = cp.async mma.sync always;
- *                      2 = tcgen05 whenever T <= 256; 3 = TMA-ring mma.sync wherever it exists (32 < T <= 80)
- *   "attention_ring"   1 = default; 0 = auto never picks the TMA-ring kernel (round-1 behaviour, for A/B runs).  The ring
- *                      kernel is bit-identical to the cp.async one (same fragments and order of operations)
+ *   "attention_impl"   0 = auto: the TMA-ring mma.sync kernel for 32 < T <= 80 (the 77-token CLIP text tower, dense and
+ *                      packed; the 50-token vision tower; 64-token SigLIP text), the tcgen05 attention kernel for
+ *                      T <= 32 and 128 < T <= 256 (SigLIP vision), the cp.async mma.sync kernel otherwise;
+ *                      1 = cp.async mma.sync always; 2 = tcgen05 whenever T <= 256; 3 = TMA-ring wherever it exists
+ *   "attention_ring"   1 = default; 0 = auto never picks the TMA-ring kernel (tcgen05 for T <= 64, cp.async mma.sync for
+ *                      the text tower: the round-1 choice, for A/B runs).  The ring kernel is bit-identical to the
+ *                      cp.async one (same fragments and order of operations)
  *   "pdl"              1 = every kernel is launched with programmatic stream serialization (prologues overlap the
  *                      previous kernel's tail)
  *   "graph_max_batch"  forwards with B <= this are replayed as one CUDA graph from the third call of a shape on

@@ -23,9 +23,10 @@
 // traffic (80 us first version, 72 with interleaved chains, 66 with the rotating row blocks).
 // Tried and dropped: a contiguous run of items per CTA instead of round-robin (same 80 us at that stage: DRAM page
 // locality is not the limit), mbarrier.try_wait with a suspend-time hint (same duration, same instruction count).
-// Rows of the box beyond the sequence (T .. 16*ceil(T/16)-1) belong to the next sample or to stale arena memory; their
-// keys are masked by a select, their V rows are zeroed in shared memory before P V so that a non-finite neighbour can
-// never leak into this sample (0 * NaN) -- the semantics stay those of attention.cuh / SDPA safe softmax.
+// Rows T .. 16*ceil(T/16)-1 of a stage hold the next sample's rows (packed mode: the box is a multiple of 16 rows) or
+// whatever an earlier item left there (fixed-length mode: the box is exactly T rows); their keys are masked by a
+// select, their V rows are zeroed in shared memory before P V so that a non-finite neighbour can never leak into this
+// sample (0 * NaN) -- the semantics stay those of attention.cuh / SDPA safe softmax.
 #pragma once
 #include "attention.cuh"
 #include "gemm_tcgen05.cuh"
@@ -34,7 +35,7 @@ namespace mmcm {
 
 constexpr int ATR_MAXBOX = 8;
 struct AttRingMaps {
-  CUtensorMap m[ATR_MAXBOX];   // m[k]: box of 64 dh x 16*(k+1) rows over qkv [rows, 3*D]
+  CUtensorMap m[ATR_MAXBOX];   // m[k]: box of 64 dh x 16*(k+1) rows over qkv [rows, 3*D] (fixed-length mode: T rows)
 };
 
 template <int TPAD, int NG, int NSTAGES>
@@ -286,7 +287,9 @@ attention_ring_kernel(const __grid_constant__ AttRingMaps maps, __nv_bfloat16* _
         const uint32_t full = bars + 16 * stage;
         const uint32_t dst = base + stage * C::STAGE_BYTES;
         const int c = (item % heads) * ATT_DH;
-        mbar_expect_tx(full, (uint32_t)(3 * nb * 16 * 128));
+        // fixed-length mode: the box is exactly T rows (nothing of the next sample is fetched); packed: 16 nb rows
+        const int box_rows = seq_start ? nb * 16 : T_fixed;
+        mbar_expect_tx(full, (uint32_t)(3 * box_rows * 128));
         tma_load_2d(&maps.m[nb - 1], full, dst, c, m0.row0);
         tma_load_2d(&maps.m[nb - 1], full, dst + C::TILE_BYTES, D + c, m0.row0);
         tma_load_2d(&maps.m[nb - 1], full, dst + 2 * C::TILE_BYTES, 2 * D + c, m0.row0);

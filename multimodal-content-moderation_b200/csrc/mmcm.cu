@@ -441,7 +441,8 @@ static int launch_att_ring(const bf16* qkv, bf16* out, const uint8_t* kvalid, in
   const int D = heads * ATT_DH;
   AttRingMaps maps;
   memset(&maps, 0, sizeof(maps));
-  for (int k = 0; k < C::QW; ++k) CKR(get_tmap(&maps.m[k], qkv, (int64_t)B * T, 3 * D, 16 * (k + 1), false));
+  for (int k = 0; k < C::QW; ++k)
+    CKR(get_tmap(&maps.m[k], qkv, (int64_t)B * T, 3 * D, seq_start ? 16 * (k + 1) : std::min(T, 16 * (k + 1)), false));
   const int total = B * heads;
   int grid = g_num_sms;
   if (grid > total) grid = total;
@@ -497,13 +498,19 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
   if (B <= 0) return MMCM_OK;
   const bool tc128 = T <= 128 && (t_opts->attention_impl == 2 || (t_opts->attention_impl == 0 && T <= 64 && !seq_start));
   const bool tc256 = T > 128 && T <= 256 && !seq_start && t_opts->attention_impl != 1;
-  // 3 = TMA-ring mma.sync kernel wherever it is instantiated (32 < T <= 80); auto picks it for the 77-token text tower,
-  // dense and packed alike (so the two stay bit-identical)
-  const int ring = (t_opts->attention_impl == 3 && T > 32 && T <= 80) ? (T <= 64 ? 64 : 80)
-                   : (t_opts->attention_impl == 0 && T > 64 && T <= 80 && t_opts->attention_ring) ? 80 : 0;
+  // TMA-ring mma.sync kernel (32 < T <= 80): auto (with attention_ring = 1) and attention_impl 3; the 77-token text
+  // tower runs it dense and packed alike (so the two stay bit-identical), the 50-token vision tower dense
+  const bool ring_ok = T > 32 && T <= 80 &&
+                       (t_opts->attention_impl == 3 || (t_opts->attention_impl == 0 && t_opts->attention_ring));
+  const int ring = ring_ok ? (T <= 64 ? 64 : 80) : 0;
   if (ring) {
+    // consumer groups x ring stages, measured per 1024 samples (ncu, profiles/r02_attention_ring_ncu.txt):
+    //   77-token causal text  <80, NG, 7>: NG = 2 / 3 / 4 -> 72.5 / 59.1 / 64.0 us (3 groups compute, 4 stages in flight,
+    //                                      16 warps -> 128 registers, no spills)
+    //   50-token vision       <64, NG, S>: <3, 9> / <4, 9> / <5, 8> -> 90.5 / 84.3 / 78.6 us (every warp multiplies all keys:
+    //                                      the more warps the better; the tcgen05 kernel: 82.8 us)
     if (ring == 64) CKR((launch_att_ring<64, 5, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
-    else CKR((launch_att_ring<80, 4, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
+    else CKR((launch_att_ring<80, 3, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
     if (stats) stats->launches++;
     return MMCM_OK;
   }

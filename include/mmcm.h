@@ -128,6 +128,20 @@ MMCM_API int mmcm_forward_host_u8(mmcm_handle h, const int64_t* input_ids, const
                          const float* image_present, int32_t B, int32_t S, float* logits_out, float* probs_out,
                          void* stream);
 
+/* Double-buffered input pipeline for callers that score batch after batch (the reference's evaluate() loop over a
+ * DataLoader with pin_memory, R/scripts/evaluate.py:163-183): enqueue the host->device copies of the NEXT batch now, on
+ * the handle's copy stream and into a second set of input buffers, then call mmcm_forward_host* for the CURRENT batch --
+ * the copies run on the copy engine while the towers compute.  The following mmcm_forward_host* call that is given the
+ * SAME host pointers, B and S finds its inputs on the device (it waits for the per-stage copy events only) and issues no
+ * copies of its own; any other call ignores and drops the prefetched batch.  The host buffers must stay untouched until
+ * that forward returns.  Logits are bit-identical with and without the prefetch.  One batch can be in flight. */
+MMCM_API int mmcm_prefetch_host(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                                const float* pixel_values, const float* text_present, const float* image_present,
+                                int32_t B, int32_t S);
+MMCM_API int mmcm_prefetch_host_u8(mmcm_handle h, const int64_t* input_ids, const int64_t* attention_mask,
+                                   const uint8_t* pixels_u8, const float* text_present, const float* image_present,
+                                   int32_t B, int32_t S);
+
 /* Introspection ------------------------------------------------------------------------------ */
 /* Copies an intermediate of the LAST forward into dst (device fp32).  (With "skip_absent_text" the text rows of samples
  * whose text cannot reach the logits hold the BOS row's output, not the reference's pooler output.)  Names: "text_pooled",

@@ -152,6 +152,30 @@ class Engine:
                                            ip.data_ptr(), B, S, logits.data_ptr(), _ptr(probs), C.c_void_p(stream)))
         return (logits, probs) if want_probs else logits
 
+    def prefetch_host(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], pixels: torch.Tensor,
+                      text_present: torch.Tensor, image_present: torch.Tensor) -> None:
+        """Ship the NEXT batch to the device now (copy engine), then call `forward_host` / `forward_host_u8` for the
+        current one: the following forward_host* call on these SAME tensors finds its inputs on the device.  `pixels`
+        is the fp32 `pixel_values` tensor or the uint8 HWC image tensor.  The tensors must be host tensors of the final
+        dtype (int64 ids / mask, fp32 flags), contiguous -- no conversion copy may sit between them and the call that
+        consumes them -- and are kept alive by the engine until then."""
+        want = ((input_ids, torch.int64), (attention_mask, torch.int64), (text_present, torch.float32),
+                (image_present, torch.float32))
+        for t, dt in want:
+            if t is not None and (t.is_cuda or t.dtype != dt or not t.is_contiguous()):
+                raise ValueError("prefetch_host needs contiguous host tensors of dtype int64 (ids, mask) / float32 (flags)")
+        if pixels.is_cuda or not pixels.is_contiguous() or pixels.dtype not in (torch.float32, torch.uint8):
+            raise ValueError("prefetch_host needs a contiguous host fp32 pixel_values or uint8 image tensor")
+        B, S = input_ids.shape
+        if pixels.dtype == torch.uint8:
+            self._check_u8(pixels, B)
+            fn = self.lib.mmcm_prefetch_host_u8
+        else:
+            fn = self.lib.mmcm_prefetch_host
+        L.check(fn(self._h, input_ids.data_ptr(), _ptr(attention_mask), pixels.data_ptr(), text_present.data_ptr(),
+                   image_present.data_ptr(), B, S))
+        self._prefetched = (input_ids, attention_mask, pixels, text_present, image_present)
+
     # ------------------------------------------------------------------ uint8 pixel source (SURVEY 8f rank 1)
     def _check_u8(self, images_u8: torch.Tensor, B: int) -> torch.Tensor:
         a = self.arch

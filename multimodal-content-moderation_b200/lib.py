@@ -45,6 +45,8 @@ _SIGS = {
     "mmcm_forward_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_forward_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmcm_forward_host_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "mmcm_prefetch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32]),
+    "mmcm_prefetch_host_u8": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32]),
     "mmcm_get_stage": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "mmcm_last_launch_count": (C.c_int64, [_P]),
     "mmcm_last_host_copy_share": (C.c_double, [_P]),

@@ -185,6 +185,51 @@ def test_forward_host_end_to_end_call():
     assert (host - dev).abs().max().item() <= 1e-5
 
 
+def test_prefetch_host_pipeline_is_bit_identical():
+    """mmcm_prefetch_host(next batch) + mmcm_forward_host(current batch): the double-buffered input pipeline returns
+    exactly the logits of the plain calls, whatever the order of prefetches, hits, misses and batch sizes."""
+    from mmcm_b200 import synthetic as syn
+    kind, a, kw, sd, _, _ = build_case("clip_fusion_hardened")
+    m = _make_module(kind, a, kw, sd)
+    m.set_option("micro_batch", 24)
+    eng = m._ensure_engine(0)
+    sets = [{k: v.pin_memory() for k, v in syn.make_inputs(a, B, seed=s, edge_rows=True).items()}
+            for B, s in ((40, 1), (40, 2), (56, 3), (9, 4), (40, 5))]
+    args = lambda d: (d["input_ids"], d["attention_mask"], d["pixel_values"], d["text_present"], d["image_present"])
+    plain = [eng.forward_host(*args(d)).clone() for d in sets]
+    # the steady-state pattern: prefetch i+1, then forward i
+    eng.prefetch_host(*args(sets[0]))
+    got = []
+    for i in range(len(sets)):
+        if i + 1 < len(sets):
+            eng.prefetch_host(*args(sets[i + 1]))
+        got.append(eng.forward_host(*args(sets[i])).clone())
+    for g, p in zip(got, plain):
+        assert torch.equal(g, p)
+    # a prefetched batch that is never consumed, a forward of something else in between, a late consumer
+    eng.prefetch_host(*args(sets[2]))
+    assert torch.equal(eng.forward_host(*args(sets[0])), plain[0])          # miss: plain path, prefetched set untouched
+    assert torch.equal(eng.forward_host(*args(sets[2])), plain[2])          # still a hit
+    eng.prefetch_host(*args(sets[1]))
+    eng.prefetch_host(*args(sets[3]))                                       # promotes 1, ships 3
+    eng.prefetch_host(*args(sets[4]))                                       # 1 is dropped, 3 promoted, 4 shipped
+    assert torch.equal(eng.forward_host(*args(sets[1])), plain[1])          # miss
+    assert torch.equal(eng.forward_host(*args(sets[4])), plain[4])
+    # uint8 pixels
+    img = torch.randint(0, 256, (40, a.image, a.image, 3), dtype=torch.uint8,
+                        generator=torch.Generator().manual_seed(3)).pin_memory()
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    d = sets[0]
+    want = eng.forward_host_u8(d["input_ids"], d["attention_mask"], img, mean, std, d["text_present"],
+                               d["image_present"]).clone()
+    eng.prefetch_host(d["input_ids"], d["attention_mask"], img, d["text_present"], d["image_present"])
+    assert torch.equal(eng.forward_host_u8(d["input_ids"], d["attention_mask"], img, mean, std, d["text_present"],
+                                           d["image_present"]), want)
+    with pytest.raises(ValueError, match="prefetch_host needs"):
+        eng.prefetch_host(d["input_ids"].int(), d["attention_mask"], d["pixel_values"], d["text_present"],
+                          d["image_present"])
+
+
 def test_full_size_properties_batch_256():
     """BASELINE config sizes (B=256): finite, permutation-equivariant over samples, split-invariant."""
     from mmcm_b200 import synthetic as syn

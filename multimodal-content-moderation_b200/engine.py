@@ -176,6 +176,22 @@ class Engine:
                    image_present.data_ptr(), B, S))
         self._prefetched = (input_ids, attention_mask, pixels, text_present, image_present)
 
+    def score_host_batches(self, batches, want_probs: bool = False):
+        """The reference's evaluation loop (R/scripts/evaluate.py:163-183: `for batch in loader: model(**batch)`) over
+        HOST batches -- dicts with the collate_fn keys of R/src/data/dataset.py:171-193, pinned tensors of the final
+        dtypes (what a `DataLoader(pin_memory=True)` yields) -- as a generator of host logits (or (logits, probs)), one
+        per batch: batch i+1 is shipped with `prefetch_host` while batch i is scored, so the H2D copies run on the copy
+        engine behind the towers.  Same logits, bit for bit, as one `forward_host` per batch."""
+        order = ("input_ids", "attention_mask", "pixel_values", "text_present", "image_present")
+        it = iter(batches)
+        cur = next(it, None)
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self.prefetch_host(*[nxt.get(k) for k in order])
+            yield self.forward_host(*[cur.get(k) for k in order], want_probs=want_probs)
+            cur = nxt
+
     # ------------------------------------------------------------------ uint8 pixel source (SURVEY 8f rank 1)
     def _check_u8(self, images_u8: torch.Tensor, B: int) -> torch.Tensor:
         a = self.arch

@@ -206,6 +206,8 @@ def test_prefetch_host_pipeline_is_bit_identical():
         got.append(eng.forward_host(*args(sets[i])).clone())
     for g, p in zip(got, plain):
         assert torch.equal(g, p)
+    for g, p in zip(eng.score_host_batches(sets), plain):                   # the same pattern as a generator
+        assert torch.equal(g, p)
     # a prefetched batch that is never consumed, a forward of something else in between, a late consumer
     eng.prefetch_host(*args(sets[2]))
     assert torch.equal(eng.forward_host(*args(sets[0])), plain[0])          # miss: plain path, prefetched set untouched

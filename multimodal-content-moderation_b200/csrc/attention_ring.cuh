@@ -9,7 +9,8 @@
 // hides 40 % of them.  Here:
 //
 //   warp NG*QW   producer: per item one header (validity bit words, length, first row, head) and three TMA boxes
-//                (Q | K | V: 16*ceil(T/16) rows x 64 dh, 128B swizzle) into the next stage of an NSTAGES-deep ring;
+//                (Q | K | V: 64 dh x T rows, or 16*ceil(T/16) rows for packed text; 128B swizzle) into the next stage of
+//                an NSTAGES-deep ring;
 //                the metadata of the following items is loaded two and three iterations ahead
 //   NG groups    of QW = TPAD/16 consumer warps; group g takes every NG-th item of the CTA.  Warp w of a group owns
 //                query rows 16w .. 16w+15 exactly as in attention.cuh (same fragments, same order of operations: the
@@ -18,9 +19,10 @@
 //                tile is transposed through the warp's own (dead) Q rows and stored as 128-byte lines, and no block
 //                barrier exists: a stage is handed over through one full / one empty mbarrier.
 //
-// One persistent CTA per SM (7 x 30 KB stages for the text tower): three items in flight while four are computed.
-// Measured (ncu, 1024 x 77 x 8 heads, profiles/r02_attention_ring_ncu.txt): 96.7 -> 66.4 us = 4.6 TB/s of DRAM
-// traffic (80 us first version, 72 with interleaved chains, 66 with the rotating row blocks).
+// One persistent CTA per SM.  Text tower <80, 3, 7>: 7 x 30 KB stages, four items in flight while three are computed,
+// 16 warps -> 128 registers.  Measured (ncu, 1024 x 77 x 8 heads, profiles/r02_attention_ring_ncu.txt): 96.7 -> 60 us =
+// 4.95 TB/s of DRAM traffic = 76 % of the measured HBM peak (80 us first version, 72 with interleaved chains, 66 with
+// the rotating row blocks, 59-60 with three consumer groups instead of four).  Vision tower <64, 5, 8>: 79 us.
 // Tried and dropped: a contiguous run of items per CTA instead of round-robin (same 80 us at that stage: DRAM page
 // locality is not the limit), mbarrier.try_wait with a suspend-time hint (same duration, same instruction count).
 // Rows T .. 16*ceil(T/16)-1 of a stage hold the next sample's rows (packed mode: the box is a multiple of 16 rows) or

@@ -638,6 +638,7 @@ def main():
                            "micro_batch": args.micro_batch or "library default", "streams": args.streams, "pdl": args.pdl,
                            "numa_node_rank0": numa,
                            "varlen_text": args.varlen, "pooled_last_layer": args.pooled_last, "ln_fold": args.ln_fold,
+                           "attention_impl": args.attention_impl, "attention_ring": args.attention_ring,
                            "algorithmic_gflop_per_sample": flops["total"] / 1e9},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps), "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu, "parity": parity, "extras": extras}

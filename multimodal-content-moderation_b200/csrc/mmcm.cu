@@ -507,8 +507,9 @@ static int launch_attention(const bf16* qkv, const uint8_t* kvalid, int B, int T
     // consumer groups x ring stages, measured per 1024 samples (ncu, profiles/r02_attention_ring_ncu.txt):
     //   77-token causal text  <80, NG, 7>: NG = 2 / 3 / 4 -> 72.5 / 59.1 / 64.0 us (3 groups compute, 4 stages in flight,
     //                                      16 warps -> 128 registers, no spills)
-    //   50-token vision       <64, NG, S>: <3, 9> / <4, 9> / <5, 8> -> 90.5 / 84.3 / 78.6 us (every warp multiplies all keys:
-    //                                      the more warps the better; the tcgen05 kernel: 82.8 us)
+    //   50-token vision       <64, NG, S>: <3, 9> / <4, 9> / <5, 8> / <6, 9> -> 90.5 / 84.3 / 78.6 / 83 us (every warp multiplies
+    //                                      all keys: more warps help until 25 warps cap the registers at 72 and leave
+    //                                      three stages in flight; the tcgen05 kernel: 82.8 us)
     if (ring == 64) CKR((launch_att_ring<64, 5, 8>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
     else CKR((launch_att_ring<80, 3, 7>(qkv, out, kvalid, B, T, heads, causal, st, seq_start, seq_len)));
     if (stats) stats->launches++;
